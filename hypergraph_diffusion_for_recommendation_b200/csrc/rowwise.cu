@@ -1,0 +1,141 @@
+// Row-wise backward of the fused propagation epilogue (LayerNorm o LeakyReLU), sm_100a.
+//
+// Forward (spmm.cu finish_row): a = leaky_relu(pre); y = (a - mean) * rstd * gamma + beta, the
+// lns[k](HGCNConv(...)) pattern of model/graph/HGNN_HD3.py:421,710,714.  Given dy this produces
+// dpre and the parameter gradients dgamma = sum_rows dy * xhat, dbeta = sum_rows dy.  The column
+// sums are accumulated per block in a fixed row order, written to `partials`, and added up by a
+// second kernel in block order: no atomics, bit-reproducible.
+#include "hgr_internal.cuh"
+
+namespace hgr {
+
+constexpr int kRwThreads = 256;
+constexpr int kMaxPartialBlocks = 1184;  // 8 per SM on a 148-SM B200
+
+template <int LPR>
+__global__ void __launch_bounds__(kRwThreads) leaky_ln_bwd_kernel(const float4 *__restrict__ pre,
+                                                                   const float4 *__restrict__ dy,
+                                                                   const float *__restrict__ gamma, float eps,
+                                                                   int use_leaky, float slope, int64_t n_rows,
+                                                                   float4 *__restrict__ dpre,
+                                                                   float *__restrict__ partials) {
+    constexpr int GPB = kRwThreads / LPR;
+    constexpr int D = LPR * 4;
+    constexpr float kInvD = 1.0f / (float)D;
+    const int gl = threadIdx.x % LPR;
+    const int g = threadIdx.x / LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
+    float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gamma) gm = __ldg(reinterpret_cast<const float4 *>(gamma) + gl);
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg;
+    for (int64_t row = (int64_t)blockIdx.x * GPB + g; row < n_rows; row += (int64_t)gridDim.x * GPB) {
+        const int64_t off = row * LPR + gl;
+        const float4 p = ld_stream_f4(pre + off);
+        float4 go = ld_stream_f4(dy + off);
+        float4 a = p;
+        if (use_leaky) {
+            a.x = p.x > 0.f ? p.x : p.x * slope;
+            a.y = p.y > 0.f ? p.y : p.y * slope;
+            a.z = p.z > 0.f ? p.z : p.z * slope;
+            a.w = p.w > 0.f ? p.w : p.w * slope;
+        }
+        float4 da = go;
+        if (gamma) {
+            const float mean = group_sum<LPR>((a.x + a.y) + (a.z + a.w), gmask) * kInvD;
+            const float cx = a.x - mean, cy = a.y - mean, cz = a.z - mean, cw = a.w - mean;
+            const float var = group_sum<LPR>((cx * cx + cy * cy) + (cz * cz + cw * cw), gmask) * kInvD;
+            const float rstd = 1.0f / sqrtf(var + eps);
+            const float hx = cx * rstd, hy = cy * rstd, hz = cz * rstd, hw = cw * rstd;
+            sg.x += go.x * hx;
+            sg.y += go.y * hy;
+            sg.z += go.z * hz;
+            sg.w += go.w * hw;
+            sb.x += go.x;
+            sb.y += go.y;
+            sb.z += go.z;
+            sb.w += go.w;
+            const float tx = go.x * gm.x, ty = go.y * gm.y, tz = go.z * gm.z, tw = go.w * gm.w;
+            const float m1 = group_sum<LPR>((tx + ty) + (tz + tw), gmask) * kInvD;
+            const float m2 = group_sum<LPR>((tx * hx + ty * hy) + (tz * hz + tw * hw), gmask) * kInvD;
+            da.x = rstd * (tx - m1 - hx * m2);
+            da.y = rstd * (ty - m1 - hy * m2);
+            da.z = rstd * (tz - m1 - hz * m2);
+            da.w = rstd * (tw - m1 - hw * m2);
+        }
+        if (use_leaky) {
+            da.x = p.x > 0.f ? da.x : da.x * slope;
+            da.y = p.y > 0.f ? da.y : da.y * slope;
+            da.z = p.z > 0.f ? da.z : da.z * slope;
+            da.w = p.w > 0.f ? da.w : da.w * slope;
+        }
+        dpre[off] = da;
+    }
+    if (!gamma) return;
+    // block reduction over the GPB groups in group order
+    __shared__ float4 sh[2][kRwThreads];
+    sh[0][threadIdx.x] = sg;
+    sh[1][threadIdx.x] = sb;
+    __syncthreads();
+    if (g == 0) {
+        float4 tg = sh[0][gl], tb = sh[1][gl];
+        for (int k = 1; k < GPB; ++k) {
+            const float4 ug = sh[0][k * LPR + gl], ub = sh[1][k * LPR + gl];
+            tg.x += ug.x; tg.y += ug.y; tg.z += ug.z; tg.w += ug.w;
+            tb.x += ub.x; tb.y += ub.y; tb.z += ub.z; tb.w += ub.w;
+        }
+        float4 *out = reinterpret_cast<float4 *>(partials + (size_t)blockIdx.x * 2 * D);
+        out[gl] = tg;
+        out[LPR + gl] = tb;
+    }
+}
+
+__global__ void ln_param_grad_reduce_kernel(const float *__restrict__ partials, int n_blocks, int D,
+                                            float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * D) return;
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * 2 * D + k];
+    if (k < D) dgamma[k] = s;
+    else dbeta[k - D] = s;
+}
+
+}  // namespace hgr
+
+extern "C" {
+
+int32_t hgr_ln_bwd_partial_rows(int64_t n_rows) {
+    int64_t b = hgr::ceil_div(n_rows, 64);
+    if (b < 1) b = 1;
+    if (b > hgr::kMaxPartialBlocks) b = hgr::kMaxPartialBlocks;
+    return (int32_t)b;
+}
+
+int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
+                         float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
+                         float *partials, hgr_stream_t stream) {
+    using namespace hgr;
+    HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
+    HGR_REQUIRE(n_rows >= 0, "n_rows negative");
+    if (n_rows == 0) return HGR_OK;
+    HGR_REQUIRE(pre && dy && dpre, "pre, dy or dpre is NULL");
+    HGR_REQUIRE(aligned16(pre) && aligned16(dy) && aligned16(dpre) && aligned16(gamma) && aligned16(partials),
+                "operands must be 16-byte aligned");
+    HGR_REQUIRE(gamma == nullptr || (dgamma && dbeta && partials), "LayerNorm backward needs dgamma, dbeta and partials");
+    const int blocks = hgr_ln_bwd_partial_rows(n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4 *p4 = reinterpret_cast<const float4 *>(pre), *g4 = reinterpret_cast<const float4 *>(dy);
+    float4 *o4 = reinterpret_cast<float4 *>(dpre);
+    switch (D) {
+        case 32: leaky_ln_bwd_kernel<8><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials); break;
+        case 64: leaky_ln_bwd_kernel<16><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials); break;
+        default: leaky_ln_bwd_kernel<32><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials); break;
+    }
+    HGR_LAUNCH_OK("leaky_ln_bwd_kernel");
+    if (gamma) {
+        ln_param_grad_reduce_kernel<<<(2 * D + 127) / 128, 128, 0, st>>>(partials, blocks, D, dgamma, dbeta);
+        HGR_LAUNCH_OK("ln_param_grad_reduce_kernel");
+    }
+    return HGR_OK;
+}
+
+}  // extern "C"

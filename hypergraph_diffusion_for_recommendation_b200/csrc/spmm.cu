@@ -1,0 +1,308 @@
+// Sparse embedding propagation Y = epilogue(A . X) for sm_100a.
+//
+// Replaces torch.sparse.mm(adj, X) at model/graph/LightGCN.py:133, HCCF.py:199,
+// HGNN_HD3.py:549-553 of the reference, plus the elementwise / LayerNorm / residual / readout
+// kernels torch launches after it.
+//
+// Mapping.  One embedding row is D fp32 = D/4 128-bit words, so a "row group" of LPR = D/4 lanes
+// owns one output row and every gathered X row is a single fully coalesced 128-bit-per-lane load
+// (D = 64: a half warp reads one 256-byte row, a warp works on two output rows).  The group walks
+// its nonzeros in stored order and keeps ONE accumulator chain per feature, so a row that is not
+// split is accumulated with exactly the fused multiply-add sequence of the CPU oracle
+// (oracle/hgr_oracle.c) and is bit-identical to it.  Memory-level parallelism comes from issuing
+// the gathers of 8 consecutive nonzeros before the 8 dependent FMAs and from prefetching the next
+// (column, value) batch, not from splitting the sum.
+//
+// Power-law rows.  Rows longer than plan.chunk_nnz are cut into chunks of chunk_nnz nonzeros; a
+// chunk is accumulated by one group into a partial row, and a second kernel adds the partials of a
+// row in chunk order and runs the epilogue.  No atomics: results are reproducible run to run.
+// The chunk blocks are placed first in the grid because the reduce kernel waits for them.
+#include <string.h>
+
+#include "hgr_internal.cuh"
+
+namespace hgr {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 8;
+
+template <int LPR>
+__device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ idx, const float *__restrict__ val,
+                                                    const float4 *__restrict__ X4, int64_t s, int64_t e, int gl,
+                                                    unsigned gmask) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = 0;
+    float v = 0.f;
+    if (s + gl < e) {
+        c = ld_stream_i32(idx + s + gl);
+        v = ld_stream_f32(val + s + gl);
+    }
+    for (int64_t base = s; base < e; base += LPR) {
+        // prefetch the next batch of (column, value) pairs while this one is consumed
+        int cn = 0;
+        float vn = 0.f;
+        const int64_t pn = base + LPR + gl;
+        if (pn < e) {
+            cn = ld_stream_i32(idx + pn);
+            vn = ld_stream_f32(val + pn);
+        }
+        const int cnt = (int)(e - base < (int64_t)LPR ? e - base : (int64_t)LPR);
+#pragma unroll
+        for (int k0 = 0; k0 < LPR; k0 += kUnroll) {
+            if (k0 < cnt) {
+                float4 xv[kUnroll];
+                float vv[kUnroll];
+#pragma unroll
+                for (int k = 0; k < kUnroll; ++k) {
+                    const int cc = __shfl_sync(gmask, c, k0 + k, LPR);
+                    vv[k] = __shfl_sync(gmask, v, k0 + k, LPR);
+                    if (k0 + k < cnt) xv[k] = ld_ro_f4(X4 + (int64_t)cc * LPR + gl);
+                }
+#pragma unroll
+                for (int k = 0; k < kUnroll; ++k) {
+                    if (k0 + k < cnt) {
+                        acc.x = fmaf(vv[k], xv[k].x, acc.x);
+                        acc.y = fmaf(vv[k], xv[k].y, acc.y);
+                        acc.z = fmaf(vv[k], xv[k].z, acc.z);
+                        acc.w = fmaf(vv[k], xv[k].w, acc.w);
+                    }
+                }
+            }
+        }
+        c = cn;
+        v = vn;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+template <int LPR>
+__device__ __forceinline__ void finish_row(float4 acc, int64_t row, int gl, unsigned gmask, const hgr_epilogue_t &ep,
+                                           float *__restrict__ Y) {
+    constexpr float kInvD = 1.0f / (float)(LPR * 4);
+    const int64_t off = row * LPR + gl;
+    if (ep.pre) reinterpret_cast<float4 *>(ep.pre)[off] = acc;
+    if (ep.use_leaky) {
+        acc.x = leaky(acc.x, ep.leaky_slope);
+        acc.y = leaky(acc.y, ep.leaky_slope);
+        acc.z = leaky(acc.z, ep.leaky_slope);
+        acc.w = leaky(acc.w, ep.leaky_slope);
+    }
+    if (ep.ln_gamma) {
+        const float mean = group_sum<LPR>((acc.x + acc.y) + (acc.z + acc.w), gmask) * kInvD;
+        const float dx = acc.x - mean, dy = acc.y - mean, dz = acc.z - mean, dw = acc.w - mean;
+        const float var = group_sum<LPR>((dx * dx + dy * dy) + (dz * dz + dw * dw), gmask) * kInvD;
+        const float rstd = 1.0f / sqrtf(var + ep.ln_eps);
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(ep.ln_gamma) + gl);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.ln_beta) + gl);
+        acc.x = dx * rstd * g.x + b.x;
+        acc.y = dy * rstd * g.y + b.y;
+        acc.z = dz * rstd * g.z + b.z;
+        acc.w = dw * rstd * g.w + b.w;
+    }
+    if (ep.residual) {
+        const float4 r = ld_stream_f4(reinterpret_cast<const float4 *>(ep.residual) + off);
+        acc.x += r.x;
+        acc.y += r.y;
+        acc.z += r.z;
+        acc.w += r.w;
+    }
+    if (ep.n_addends > 0) {
+        float4 s = ld_stream_f4(reinterpret_cast<const float4 *>(ep.addends[0]) + off);
+#pragma unroll
+        for (int j = 1; j < HGR_MAX_ADDENDS; ++j) {  // constant indices keep ep in param space
+            if (j < ep.n_addends) {
+                const float4 a = ld_stream_f4(reinterpret_cast<const float4 *>(ep.addends[j]) + off);
+                s.x += a.x;
+                s.y += a.y;
+                s.z += a.z;
+                s.w += a.w;
+            }
+        }
+        acc.x += s.x;
+        acc.y += s.y;
+        acc.z += s.z;
+        acc.w += s.w;
+    }
+    if (ep.n_addends > 0 || ep.scale_always) {
+        acc.x *= ep.scale;
+        acc.y *= ep.scale;
+        acc.z *= ep.scale;
+        acc.w *= ep.scale;
+    }
+    reinterpret_cast<float4 *>(Y)[off] = acc;
+}
+
+// grid = [heavy chunk blocks | light row blocks]
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(hgr_csr_t A, const float4 *__restrict__ X4,
+                                                             float *__restrict__ Y, hgr_epilogue_t ep,
+                                                             float4 *__restrict__ partials, int heavy_blocks) {
+    constexpr int GPB = kThreads / LPR;
+    const int gl = threadIdx.x % LPR;
+    const int g = threadIdx.x / LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
+    if ((int)blockIdx.x < heavy_blocks) {
+        const int64_t chunk = (int64_t)blockIdx.x * GPB + g;
+        if (chunk >= A.n_chunks) return;
+        const int h = A.chunk_owner[chunk];
+        const int row = A.heavy_rows[h];
+        const int64_t s = A.indptr[row] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
+        const int64_t row_end = A.indptr[row + 1];
+        const int64_t e = s + A.chunk_nnz < row_end ? s + A.chunk_nnz : row_end;
+        const float4 acc = gather_accumulate<LPR>(A.indices, A.values, X4, s, e, gl, gmask);
+        partials[chunk * LPR + gl] = acc;
+        return;
+    }
+    const int64_t row = (int64_t)(blockIdx.x - heavy_blocks) * GPB + g;
+    if (row >= A.n_rows) return;
+    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
+    if (A.n_heavy_rows > 0 && e - s > (int64_t)A.chunk_nnz) return;  // summed by spmm_heavy_reduce_kernel
+    const float4 acc = gather_accumulate<LPR>(A.indices, A.values, X4, s, e, gl, gmask);
+    finish_row<LPR>(acc, row, gl, gmask, ep, Y);
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A, const float4 *__restrict__ partials,
+                                                                     float *__restrict__ Y, hgr_epilogue_t ep) {
+    constexpr int GPB = kThreads / LPR;
+    const int gl = threadIdx.x % LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
+    const int h = blockIdx.x * GPB + threadIdx.x / LPR;
+    if (h >= A.n_heavy_rows) return;
+    const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t c = c0; c < c1; c += kUnroll) {
+        float4 p[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k)
+            if (c + k < c1) p[k] = ld_stream_f4(partials + (c + k) * LPR + gl);
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k)
+            if (c + k < c1) {
+                acc.x += p[k].x;
+                acc.y += p[k].y;
+                acc.z += p[k].z;
+                acc.w += p[k].w;
+            }
+    }
+    finish_row<LPR>(acc, A.heavy_rows[h], gl, gmask, ep, Y);
+}
+
+static int check_csr(const hgr_csr_t *A, const char *name) {
+    HGR_REQUIRE(A != nullptr, "%s is NULL", name);
+    HGR_REQUIRE(A->n_rows >= 0 && A->n_cols >= 0 && A->nnz >= 0, "%s: negative dimension", name);
+    HGR_REQUIRE(A->indptr && (A->nnz == 0 || (A->indices && A->values)), "%s: NULL indptr/indices/values", name);
+    if (A->n_heavy_rows > 0) {
+        HGR_REQUIRE(A->chunk_nnz > 0 && A->n_chunks > 0, "%s: split plan without chunk size", name);
+        HGR_REQUIRE(A->heavy_rows && A->heavy_chunk_ptr && A->chunk_owner, "%s: NULL split-plan arrays", name);
+    }
+    return HGR_OK;
+}
+
+static int check_epilogue(const hgr_epilogue_t *ep) {
+    if (!ep) return HGR_OK;
+    HGR_REQUIRE(ep->n_addends >= 0 && ep->n_addends <= HGR_MAX_ADDENDS, "epilogue: n_addends %d out of range", ep->n_addends);
+    HGR_REQUIRE((ep->ln_gamma == nullptr) == (ep->ln_beta == nullptr), "epilogue: ln_gamma and ln_beta must come together");
+    HGR_REQUIRE(aligned16(ep->ln_gamma) && aligned16(ep->ln_beta) && aligned16(ep->residual) && aligned16(ep->pre),
+                "epilogue: operands must be 16-byte aligned");
+    for (int j = 0; j < ep->n_addends; ++j)
+        HGR_REQUIRE(ep->addends[j] && aligned16(ep->addends[j]), "epilogue: addend %d NULL or misaligned", j);
+    return HGR_OK;
+}
+
+template <int LPR>
+static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws,
+                       cudaStream_t st) {
+    constexpr int GPB = kThreads / LPR;
+    const int64_t heavy_blocks = A.n_heavy_rows > 0 ? ceil_div(A.n_chunks, GPB) : 0;
+    const int64_t light_blocks = ceil_div(A.n_rows, GPB);
+    const int64_t grid = heavy_blocks + light_blocks;
+    if (grid == 0) return HGR_OK;
+    HGR_REQUIRE(grid < (int64_t)0x7fffffff, "grid too large (%lld blocks)", (long long)grid);
+    spmm_rows_kernel<LPR><<<(unsigned)grid, kThreads, 0, st>>>(A, reinterpret_cast<const float4 *>(X), Y, ep,
+                                                               reinterpret_cast<float4 *>(ws), (int)heavy_blocks);
+    HGR_LAUNCH_OK("spmm_rows_kernel");
+    if (A.n_heavy_rows > 0) {
+        spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, GPB), kThreads, 0, st>>>(
+            A, reinterpret_cast<const float4 *>(ws), Y, ep);
+        HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
+    }
+    return HGR_OK;
+}
+
+static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi, void *ws,
+                     size_t ws_bytes, cudaStream_t st) {
+    int rc = check_csr(A, "A");
+    if (rc) return rc;
+    rc = check_epilogue(epi);
+    if (rc) return rc;
+    HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
+    HGR_REQUIRE(A->n_rows == 0 || (X && Y), "X or Y is NULL");
+    HGR_REQUIRE(aligned16(X) && aligned16(Y), "X and Y must be 16-byte aligned");
+    const size_t need = hgr_spmm_workspace_bytes(A, D);
+    if (need > 0 && (ws == nullptr || ws_bytes < need))
+        return set_error(HGR_ERR_WORKSPACE, "spmm workspace: need %zu bytes, got %zu", need, ws_bytes);
+    HGR_REQUIRE(aligned16(ws), "workspace must be 16-byte aligned");
+    hgr_epilogue_t ep;
+    if (epi) ep = *epi;
+    else {
+        memset(&ep, 0, sizeof(ep));
+        ep.scale = 1.f;
+    }
+    switch (D) {
+        case 32: return launch_spmm<8>(*A, X, Y, ep, ws, st);
+        case 64: return launch_spmm<16>(*A, X, Y, ep, ws, st);
+        default: return launch_spmm<32>(*A, X, Y, ep, ws, st);
+    }
+}
+
+}  // namespace hgr
+
+extern "C" {
+
+size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D) {
+    if (!A || A->n_heavy_rows <= 0) return 0;
+    return (size_t)A->n_chunks * (size_t)D * sizeof(float);
+}
+
+int hgr_spmm_f32(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi, void *workspace,
+                 size_t workspace_bytes, hgr_stream_t stream) {
+    return hgr::spmm_impl(A, X, Y, D, epi, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hgr_hgconv_f32(const hgr_csr_t *A, const hgr_csr_t *At, const float *X, float *tmp, float *Y, int32_t D,
+                   const hgr_epilogue_t *epi, void *workspace, size_t workspace_bytes, hgr_stream_t stream) {
+    HGR_REQUIRE(A && At, "A or At is NULL");
+    HGR_REQUIRE(A->n_cols == At->n_rows, "A is [%d, %d] but At is [%d, %d]", A->n_rows, A->n_cols, At->n_rows, At->n_cols);
+    HGR_REQUIRE(tmp != nullptr || At->n_rows == 0, "tmp is NULL");
+    int rc = hgr::spmm_impl(At, X, tmp, D, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc) return rc;
+    return hgr::spmm_impl(A, tmp, Y, D, epi, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hgr_lightgcn_forward_f32(const hgr_csr_t *A, const float *E0, float *layers, float *out, int32_t n_layers, int32_t D,
+                             int32_t sum_readout, void *workspace, size_t workspace_bytes, hgr_stream_t stream) {
+    HGR_REQUIRE(A && E0 && out, "A, E0 or out is NULL");
+    HGR_REQUIRE(A->n_rows == A->n_cols, "propagation needs a square adjacency, got [%d, %d]", A->n_rows, A->n_cols);
+    HGR_REQUIRE(n_layers >= 1 && n_layers <= HGR_MAX_ADDENDS, "n_layers = %d out of range [1, %d]", n_layers, HGR_MAX_ADDENDS);
+    HGR_REQUIRE(n_layers == 1 || layers, "layers buffer is NULL");
+    const size_t tab = (size_t)A->n_rows * (size_t)D;
+    const float *cur = E0;
+    for (int k = 1; k < n_layers; ++k) {
+        float *nxt = layers + (size_t)(k - 1) * tab;
+        int rc = hgr::spmm_impl(A, cur, nxt, D, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc) return rc;
+        cur = nxt;
+    }
+    hgr_epilogue_t ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.n_addends = n_layers;
+    ep.addends[0] = E0;
+    for (int k = 1; k < n_layers; ++k) ep.addends[k] = layers + (size_t)(k - 1) * tab;
+    ep.scale = sum_readout ? 1.0f : 1.0f / (float)(n_layers + 1);
+    return hgr::spmm_impl(A, cur, out, D, &ep, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+"""Host-side mirror of the reference's graph encoders, running on libhgr.so.
+
+Same class names, constructor arguments, ``forward`` signatures, return values and ``state_dict``
+keys as the reference modules they replace, so a ``GraphRecommender`` subclass of the reference
+keeps working when these are imported instead:
+
+===========================  ==================================================================
+``TorchGraphInterface``       base/torch_interface.py:3-19
+``LGCN_Encoder``              model/graph/LightGCN.py:104-140
+``HGCNConv``                  model/graph/HGNN_HD3.py:540-553 (18 identical copies)
+``SpAdjDropEdge``             model/graph/HCCF.py:213-226
+``MLP``                       model/layers/MLP.py:29-117
+``EquivSetConv``              model/graph/HGNN_HD3.py:655-720 (= model/layers/EquivSetConv.py:86-107)
+``EquivSetGNN``               model/graph/HGNN_HD3.py:555-610
+``LocalAwareEncoder``         model/graph/HGNN_HD3.py:352-427
+``HCCFEncoder``               model/graph/HCCF.py:136-191 (+ GCNLayer :193-199, HGNNLayer :201-211)
+===========================  ==================================================================
+
+What changes underneath: every ``torch.sparse.mm`` is ``ops.spmm`` / ``ops.hgconv`` /
+``ops.lightgcn_propagate`` on a ``DeviceCSR``; LayerNorm + residual + activation + layer readout are
+fused into the propagation kernel's epilogue.  The dense ``(U+I)^2`` copies of the adjacency that
+the reference's ``LocalAwareEncoder`` keeps (``hyper_uu``/``hyper_ii``, HGNN_HD3.py:386-387, never
+read by ``forward``) are not built.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .graph import DeviceCSR
+
+
+def _device() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
+
+
+class TorchGraphInterface(object):
+    """``convert_sparse_mat_to_tensor`` returns a ``DeviceCSR`` already resident in HBM, so the
+    ``.cuda()`` / ``.to(device)`` the reference chains onto it are no-ops."""
+
+    @staticmethod
+    def convert_sparse_mat_to_tensor(X, device=None) -> DeviceCSR:
+        if isinstance(X, DeviceCSR):
+            return X
+        return DeviceCSR.from_scipy(X, device=device or _device())
+
+    @staticmethod
+    def sparse_identity(n, device=None) -> DeviceCSR:
+        dev = device or _device()
+        return DeviceCSR(torch.arange(n + 1, dtype=torch.int64, device=dev), torch.arange(n, dtype=torch.int32, device=dev),
+                         torch.ones(n, dtype=torch.float32, device=dev), (n, n), symmetric=True)
+
+
+def _adjacency_of(data) -> DeviceCSR:
+    """``data.norm_adj`` as a DeviceCSR (built once and cached on the data object)."""
+    dev = getattr(data, "norm_adj_device", None)
+    if dev is None:
+        dev = TorchGraphInterface.convert_sparse_mat_to_tensor(data.norm_adj)
+        try:
+            data.norm_adj_device = dev
+        except AttributeError:
+            pass
+    return dev
+
+
+class LGCN_Encoder(nn.Module):
+    def __init__(self, data, emb_size, n_layers):
+        super(LGCN_Encoder, self).__init__()
+        self.data = data
+        self.latent_size = emb_size
+        self.layers = n_layers
+        self.norm_adj = data.norm_adj
+        self.embedding_dict = self._init_model()
+        self.sparse_norm_adj = _adjacency_of(data)
+
+    def _init_model(self):
+        initializer = nn.init.xavier_uniform_
+        return nn.ParameterDict({
+            'user_emb': nn.Parameter(initializer(torch.empty(self.data.n_users, self.latent_size))),
+            'item_emb': nn.Parameter(initializer(torch.empty(self.data.n_items, self.latent_size))),
+        })
+
+    def forward(self):
+        ego_embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
+        all_embeddings = ops.lightgcn_propagate(self.sparse_norm_adj, ego_embeddings, self.layers)
+        return all_embeddings[:self.data.n_users], all_embeddings[self.data.n_users:]
+
+
+class HGCNConv(nn.Module):
+    def __init__(self, leaky):
+        super(HGCNConv, self).__init__()
+        self.leaky = float(leaky)
+        self.act = nn.LeakyReLU(negative_slope=leaky)
+
+    def forward(self, adj, embs, act=True, ln=None, residual=None):
+        """``act(adj @ (adj.t() @ embs))``; ``ln`` (an ``nn.LayerNorm``) and ``residual`` fuse the
+        ``lns[k](...) + res`` the reference applies right after every call."""
+        return ops.hgconv(adj, embs, self.leaky if act else None,
+                          None if ln is None else ln.weight, None if ln is None else ln.bias, residual,
+                          1e-5 if ln is None else ln.eps)
+
+
+class SpAdjDropEdge(nn.Module):
+    """Bernoulli edge dropout with the reference's CPU random stream (``torch.rand(nnz)`` on the host
+    generator), so a seeded run keeps and rescales exactly the same edges."""
+
+    def __init__(self):
+        super(SpAdjDropEdge, self).__init__()
+
+    def forward(self, adj: DeviceCSR, keepRate, rand=None):
+        if keepRate == 1.0:
+            return adj
+        nnz = adj._nnz()
+        if rand is None:
+            rand = torch.rand(nnz)
+        mask = ((rand + keepRate).floor()).type(torch.bool).to(adj.device, non_blocking=True)
+        rows = torch.repeat_interleave(torch.arange(adj.shape[0], device=adj.device), adj.indptr[1:] - adj.indptr[:-1])
+        counts = torch.bincount(rows[mask], minlength=adj.shape[0])
+        indptr = torch.zeros(adj.shape[0] + 1, dtype=torch.int64, device=adj.device)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        return DeviceCSR(indptr, adj.indices[mask], adj.values[mask] / keepRate, adj.shape, chunk_nnz=adj.chunk_nnz)
+
+
+class MLP(nn.Module):
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout=.5, Normalization='bn', InputNorm=False):
+        super(MLP, self).__init__()
+        assert Normalization in ['bn', 'ln', 'None']
+        norm = {'bn': nn.BatchNorm1d, 'ln': nn.LayerNorm, 'None': lambda c: nn.Identity()}[Normalization]
+        self.in_channels, self.hidden_channels, self.out_channels = in_channels, hidden_channels, out_channels
+        self.lins = nn.ModuleList()
+        self.normalizations = nn.ModuleList()
+        self.InputNorm = InputNorm
+        self.normalizations.append(norm(in_channels) if InputNorm and Normalization != 'None' else nn.Identity())
+        if num_layers == 1:
+            self.lins.append(nn.Linear(in_channels, out_channels))
+        else:
+            self.lins.append(nn.Linear(in_channels, hidden_channels))
+            self.normalizations.append(norm(hidden_channels))
+            for _ in range(num_layers - 2):
+                self.lins.append(nn.Linear(hidden_channels, hidden_channels))
+                self.normalizations.append(norm(hidden_channels))
+            self.lins.append(nn.Linear(hidden_channels, out_channels))
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for lin in self.lins:
+            lin.reset_parameters()
+        for normalization in self.normalizations:
+            if not (normalization.__class__.__name__ == 'Identity'):
+                normalization.reset_parameters()
+
+    def forward(self, x):
+        x = self.normalizations[0](x)
+        for i, lin in enumerate(self.lins[:-1]):
+            x = lin(x)
+            x = F.relu(x, inplace=True)
+            x = self.normalizations[i + 1](x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        return self.lins[-1](x)
+
+
+class EquivSetConv(nn.Module):
+    def __init__(self, in_features, out_features, ncount, mcount, mlp1_layers=1, mlp2_layers=1, mlp3_layers=1, aggr='add',
+                 alpha=0.5, dropout=0., normalization='None', input_norm=False, hypergraph=None, data=None):
+        super().__init__()
+        self.in_features = in_features
+        self.W1 = MLP(in_features, out_features, out_features, mlp1_layers, dropout=dropout, Normalization=normalization,
+                      InputNorm=input_norm) if mlp1_layers > 0 else nn.Identity()
+        self.W2 = MLP(in_features + out_features, out_features, out_features, mlp2_layers, dropout=dropout,
+                      Normalization=normalization, InputNorm=input_norm) if mlp2_layers > 0 else None
+        self.W = MLP(out_features, out_features, out_features, mlp3_layers, dropout=dropout, Normalization=normalization,
+                     InputNorm=input_norm) if mlp3_layers > 0 else nn.Identity()
+        self.aggr = aggr
+        self.alpha = alpha
+        self.dropout = dropout
+        self.data = data
+        self.hgcn_layers = nn.ModuleList([HGCNConv(0.5) for i in range(2)])
+        self.mean_pooling = nn.AdaptiveAvgPool1d(out_features)
+        self.lns = torch.nn.ModuleList([torch.nn.LayerNorm(out_features) for i in range(2)])
+
+    def reset_parameters(self):
+        for m in (self.W1, self.W2, self.W):
+            if isinstance(m, MLP):
+                m.reset_parameters()
+
+    def forward(self, X, sparse_norm_adj, X0, ui_adj=None, act=True):
+        Xve = self.W1(X)
+        # Xe = lns[0](hgcn(A, Xve)) + Xve : one fused two-stage propagation
+        Xe = self.hgcn_layers[0](sparse_norm_adj, Xve, act=True, ln=self.lns[0], residual=Xve)
+        if self.W2 is None:
+            Xev = Xe  # the reference slices cat([X, Xe])[..., in_features:], which is Xe
+        else:
+            Xev = self.W2(torch.cat([X, Xe], -1))
+        if Xev.shape[-1] != self.mean_pooling.output_size:
+            Xev = self.mean_pooling(Xev)  # identity when the width already matches
+        X_v = self.hgcn_layers[1](sparse_norm_adj, Xev, act=True, ln=self.lns[1], residual=Xev)
+        X = X_v
+        if self.alpha != 0:
+            X = (1 - self.alpha) * X + self.alpha * X0
+        return self.W(X)
+
+
+class EquivSetGNN(nn.Module):
+    def __init__(self, num_features, args, dense_hypergraph, data, ncount, mcount):
+        super().__init__()
+        act = {'Id': nn.Identity(), 'relu': nn.ReLU(), 'prelu': nn.PReLU()}
+        self.act = act[args['activation']]
+        self.input_drop = nn.Dropout(args['input_dropout'])
+        self.dropout = nn.Dropout(args['dropout'])
+        self.data = data
+        self.in_channels = num_features
+        self.hidden_channels = args['MLP_hidden']
+        self.mlp1_layers = args['MLP_num_layers']
+        self.mlp2_layers = args['MLP_num_layers'] if args['MLP2_num_layers'] < 0 else args['MLP2_num_layers']
+        self.mlp3_layers = args['MLP_num_layers'] if args['MLP3_num_layers'] < 0 else args['MLP3_num_layers']
+        self.nlayer = args['All_num_layers']
+        self.lin_in = torch.nn.Linear(num_features, args['MLP_hidden'])
+        self.conv = EquivSetConv(args['MLP_hidden'], args['MLP_hidden'], ncount, mcount, mlp1_layers=self.mlp1_layers,
+                                 mlp2_layers=self.mlp2_layers, mlp3_layers=self.mlp3_layers, alpha=args['restart_alpha'],
+                                 aggr=args['aggregate'], dropout=args['dropout'], normalization=args['normalization'],
+                                 input_norm=args['AllSet_input_norm'], hypergraph=dense_hypergraph, data=self.data)
+
+    def reset_parameters(self):
+        self.lin_in.reset_parameters()
+        self.conv.reset_parameters()
+
+    def forward(self, x, sparse_norm_adj, n_nodes=None, ui_adj=None, act=True):
+        x = self.dropout(x)
+        x = F.relu(self.lin_in(x))
+        x0 = x
+        for i in range(self.nlayer):
+            x = self.dropout(x)
+            x = self.conv(x, sparse_norm_adj, x0, ui_adj, act)
+            x = self.act(x)
+        x = self.dropout(x)
+        return x
+
+
+class LocalAwareEncoder(nn.Module):
+    def __init__(self, data, emb_size, hyper_size, n_layers, leaky, drop_rate, device=None, use_self_att=False):
+        super(LocalAwareEncoder, self).__init__()
+        self.data = data
+        self.latent_size = emb_size
+        self.hyper_size = hyper_size
+        self.layers = n_layers
+        self.norm_adj = data.norm_adj
+        self.relu = nn.ReLU()
+        self.act = nn.LeakyReLU(leaky)
+        self.dropout = nn.Dropout(drop_rate)
+        self.edgeDropper = SpAdjDropEdge()
+        self.sparse_norm_adj = _adjacency_of(data)
+        self.edhnn_args = self.init_edhnn_config(self.hyper_size)
+        self.hgcn_layer = HGCNConv(leaky=0.3)
+        self.hgnn_layers = nn.ModuleList([HGCNConv(leaky=0.3) for i in range(self.layers)])
+        self.edhnn_layers = nn.ModuleList([EquivSetGNN(hyper_size, self.edhnn_args, self.sparse_norm_adj, self.data,
+                                                       self.data.n_users, self.data.n_items) for i in range(self.layers)])
+        self.lns = torch.nn.ModuleList([torch.nn.LayerNorm(hyper_size) for i in range(self.layers)])
+        self.edhnn_ui_n = self.data.n_users + self.data.n_items
+
+    def init_edhnn_config(self, hyper_size):
+        return {'MLP_hidden': hyper_size, 'MLP1_num_layers': 0, 'MLP2_num_layers': 0, 'MLP3_num_layers': 1, 'MLP_num_layers': 0,
+                'restart_alpha': 0.0, 'aggregate': 'mean', 'dropout': 0.5, 'normalization': 'ln', 'input_norm': True,
+                'All_num_layers': 1, 'activation': 'relu', 'input_dropout': 0.6, 'AllSet_input_norm': True}
+
+    def forward(self, ego_embeddings, sparse_norm_adj):
+        res = ego_embeddings
+        for k in range(self.layers):
+            if k != self.layers - 1:
+                ego_embeddings = self.edhnn_layers[k](ego_embeddings, sparse_norm_adj, self.edhnn_ui_n, None) + res
+            else:
+                # lns[k](hgcn(A, ego, act=False)) + res in one fused two-stage propagation; like the
+                # reference this last layer always uses the un-dropped adjacency
+                ego_embeddings = self.hgcn_layer(self.sparse_norm_adj, ego_embeddings, act=False, ln=self.lns[k], residual=res)
+        return ego_embeddings[:self.data.n_users], ego_embeddings[self.data.n_users:]
+
+
+class GCNLayer(nn.Module):
+    def __init__(self, leaky):
+        super(GCNLayer, self).__init__()
+        self.act = nn.LeakyReLU(negative_slope=leaky)
+
+    def forward(self, adj, embeds):
+        return ops.spmm(adj, embeds)
+
+
+class HGNNLayer(nn.Module):
+    def __init__(self, leaky):
+        super(HGNNLayer, self).__init__()
+        self.act = nn.LeakyReLU(negative_slope=leaky)
+
+    def forward(self, adj, embeds):
+        return torch.mm(adj, torch.mm(adj.T, embeds))
+
+
+class HCCFEncoder(nn.Module):
+    def __init__(self, conf, data):
+        super(HCCFEncoder, self).__init__()
+        self.data = data
+        self._parse_config(conf)
+        self.gcnlayer = GCNLayer(self.leaky)
+        self.hgnnlayer = HGNNLayer(self.leaky)
+        self.norm_adj = data.norm_adj
+        self.sparse_norm_adj = _adjacency_of(data)
+        self.embedding_dict = self._init_model()
+        self.drop_out = nn.Dropout(self.drop_rate)
+        self.edgeDropper = SpAdjDropEdge()
+
+    def _parse_config(self, config):
+        self.lRate = float(config['lrate'])
+        self.lr_decay = float(config['lr_decay'])
+        self.maxEpoch = int(config['max_epoch'])
+        self.batchSize = int(config['batch_size'])
+        self.reg = float(config['reg'])
+        self.latent_size = int(config['embedding_size'])
+        self.hyperDim = int(config['hyper_dim'])
+        self.drop_rate = float(config['drop_rate'])
+        self.leaky = float(config['p'])
+        self.n_layers = int(config['n_layers'])
+        self.n_edges = int(config['hyper_dim'])
+
+    def _init_model(self):
+        initializer = nn.init.xavier_uniform_
+        return nn.ParameterDict({
+            'user_emb': nn.Parameter(initializer(torch.empty(self.data.n_users, self.latent_size))),
+            'item_emb': nn.Parameter(initializer(torch.empty(self.data.n_items, self.latent_size))),
+            'user_w': nn.Parameter(initializer(torch.empty(self.latent_size, self.n_edges))),
+            'item_w': nn.Parameter(initializer(torch.empty(self.latent_size, self.n_edges))),
+        })
+
+    def forward(self, keep_rate=0.5):
+        n_users = self.data.n_users
+        embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
+        hidden = [embeddings]
+        gcn_hidden = []
+        hgnn_hidden = []
+        hyper_uu = self.embedding_dict['user_emb'] @ self.embedding_dict['user_w']
+        hyper_ii = self.embedding_dict['item_emb'] @ self.embedding_dict['item_w']
+        for i in range(self.n_layers):
+            gcn_emb = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate), hidden[-1])
+            hyper_uemb = self.hgnnlayer(self.drop_out(hyper_uu), hidden[-1][:n_users])
+            hyper_iemb = self.hgnnlayer(self.drop_out(hyper_ii), hidden[-1][n_users:])
+            gcn_hidden += [gcn_emb]
+            hgnn_hidden += [torch.cat([hyper_uemb, hyper_iemb], 0)]
+            hidden += [gcn_emb + hgnn_hidden[-1]]
+        embeddings = sum(hidden)
+        return embeddings[:n_users], embeddings[n_users:], gcn_hidden, hgnn_hidden

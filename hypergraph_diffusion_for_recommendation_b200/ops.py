@@ -1,0 +1,183 @@
+"""Propagation operators over ``DeviceCSR`` with hand-written backward passes.
+
+Each function replaces one library call site of the reference (paths relative to HD_SELFRec/):
+
+=====================  =====================================================================
+``spmm(adj, X)``        ``torch.sparse.mm(adj, X)`` -- model/graph/LightGCN.py:133, HCCF.py:199
+``hgconv(...)``         ``HGCNConv.forward`` -- model/graph/HGNN_HD3.py:540-553 (+17 copies), with the
+                        ``lns[k](...) + res`` that always follows it fused in (HGNN_HD3.py:421,710,714)
+``lightgcn_propagate``  ``LGCN_Encoder.forward`` body -- model/graph/LightGCN.py:131-136
+=====================  =====================================================================
+
+All of them run on the caller's current CUDA stream and raise if libhgr.so is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import DeviceCSR
+
+_SUPPORTED_D = (32, 64, 128)
+
+
+def _check_dense(x: torch.Tensor, rows: int, what: str) -> torch.Tensor:
+    if not x.is_cuda:
+        raise _lib.HgrError("%s must be a CUDA tensor (no CPU path)" % what)
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError("%s must be a 2-D float32 tensor, got %s %s" % (what, x.dtype, tuple(x.shape)))
+    if x.shape[0] != rows:
+        raise ValueError("%s has %d rows, the graph needs %d" % (what, x.shape[0], rows))
+    if x.shape[1] not in _SUPPORTED_D:
+        raise ValueError("embedding width %d unsupported (need one of %s)" % (x.shape[1], _SUPPORTED_D))
+    return x.contiguous()
+
+
+def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addends=(), scale=1.0, scale_always=False,
+              pre=None) -> _lib.Epilogue:
+    ep = _lib.Epilogue()
+    ep.use_leaky = 0 if slope is None else 1
+    ep.leaky_slope = 0.0 if slope is None else float(slope)
+    ep.ln_gamma, ep.ln_beta, ep.ln_eps = _lib.ptr(gamma), _lib.ptr(beta), float(eps)
+    ep.residual = _lib.ptr(residual)
+    ep.n_addends = len(addends)
+    for j, a in enumerate(addends):
+        ep.addends[j] = a.data_ptr()
+    ep.scale, ep.scale_always = float(scale), int(bool(scale_always))
+    ep.pre = _lib.ptr(pre)
+    return ep
+
+
+def _ws(a: DeviceCSR, d: int):
+    ws = a.workspace(d)
+    return (None, 0) if ws is None else (ws.data_ptr(), ws.numel() * 4)
+
+
+def spmm_raw(a: DeviceCSR, x: torch.Tensor, ep: _lib.Epilogue | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """One ``hgr_spmm_f32`` call; no autograd."""
+    x = _check_dense(x, a.shape[1], "X")
+    d = x.shape[1]
+    y = out if out is not None else torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
+    ws, ws_bytes = _ws(a, d)
+    _lib.check(_lib.lib().hgr_spmm_f32(C.byref(a.desc), x.data_ptr(), y.data_ptr(), d, None if ep is None else C.byref(ep),
+                                       ws, ws_bytes, _lib.stream_ptr()))
+    return y
+
+
+def hgconv_raw(a: DeviceCSR, at: DeviceCSR, x: torch.Tensor, ep: _lib.Epilogue | None = None) -> torch.Tensor:
+    """One ``hgr_hgconv_f32`` call: epilogue(A (At X)); no autograd."""
+    x = _check_dense(x, at.shape[1], "X")
+    d = x.shape[1]
+    tmp = torch.empty((at.shape[0], d), dtype=torch.float32, device=x.device)
+    y = torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
+    w1, b1 = _ws(a, d)
+    w2, b2 = _ws(at, d)
+    ws, ws_bytes = (w1, b1) if b1 >= b2 else (w2, b2)
+    _lib.check(_lib.lib().hgr_hgconv_f32(C.byref(a.desc), C.byref(at.desc), x.data_ptr(), tmp.data_ptr(), y.data_ptr(), d,
+                                         None if ep is None else C.byref(ep), ws, ws_bytes, _lib.stream_ptr()))
+    return y
+
+
+class _Spmm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, a):
+        ctx.a = a
+        return spmm_raw(a, x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return spmm_raw(ctx.a.t(), dy.contiguous()), None
+
+
+def spmm(adj: DeviceCSR, x: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``torch.sparse.mm(adj, x)``; backward is ``adj.t() @ dy`` through the same kernel."""
+    return _Spmm.apply(x, adj)
+
+
+class _HGConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, a, slope, eps):
+        need_pre = (slope is not None or gamma is not None) and any(ctx.needs_input_grad[:3])
+        pre = torch.empty((a.shape[0], x.shape[1]), dtype=torch.float32, device=x.device) if need_pre else None
+        g = gamma.contiguous() if gamma is not None else None
+        b = beta.contiguous() if beta is not None else None
+        r = _check_dense(residual, a.shape[0], "residual") if residual is not None else None
+        y = hgconv_raw(a, a.t(), x, _epilogue(slope=slope, gamma=g, beta=b, eps=eps, residual=r, pre=pre))
+        ctx.a, ctx.slope, ctx.eps = a, slope, eps
+        ctx.has_ln, ctx.has_res = gamma is not None, residual is not None
+        ctx.save_for_backward(pre, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        pre, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        dgamma = dbeta = None
+        if pre is not None:
+            d = dy.shape[1]
+            dz = torch.empty_like(dy)
+            if ctx.has_ln:
+                dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+                parts = torch.empty((_lib.lib().hgr_ln_bwd_partial_rows(dy.shape[0]), 2, d), dtype=torch.float32, device=dy.device)
+            else:
+                parts = None
+            _lib.check(_lib.lib().hgr_leaky_ln_bwd_f32(pre.data_ptr(), dy.data_ptr(), _lib.ptr(gamma), float(ctx.eps),
+                                                       0 if ctx.slope is None else 1, 0.0 if ctx.slope is None else float(ctx.slope),
+                                                       dy.shape[0], d, dz.data_ptr(), _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                                       _lib.ptr(parts), _lib.stream_ptr()))
+        else:
+            dz = dy
+        # y = f(A (At x))  =>  dx = At^T (A^T dz) = A (At dz) evaluated with the roles swapped
+        dx = _hgconv_transposed(ctx.a, dz) if ctx.needs_input_grad[0] else None
+        return dx, dgamma, dbeta, (dy if ctx.has_res else None), None, None, None
+
+
+def _hgconv_transposed(a: DeviceCSR, dz: torch.Tensor) -> torch.Tensor:
+    """Gradient of ``A (A^T x)`` w.r.t. ``x`` applied to ``dz``: ``A (A^T dz)`` (the operator is
+    symmetric even when A is not)."""
+    return hgconv_raw(a, a.t(), dz)
+
+
+def hgconv(adj: DeviceCSR, x: torch.Tensor, slope: float | None = None, ln_weight: torch.Tensor | None = None,
+           ln_bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, eps: float = 1e-5) -> torch.Tensor:
+    """``[LayerNorm](leaky_relu(adj @ (adj.t() @ x))) [+ residual]`` in two kernel launches.
+
+    ``slope=None`` is HGCNConv's ``act=False`` branch; ``ln_weight/ln_bias`` fuse the ``lns[k]`` that
+    wraps every HGCNConv call in the reference; ``residual`` fuses the ``+ res``."""
+    if (ln_weight is None) != (ln_bias is None):
+        raise ValueError("ln_weight and ln_bias must be given together")
+    return _HGConv.apply(x, ln_weight, ln_bias, residual, adj, slope, eps)
+
+
+def lightgcn_propagate_raw(a: DeviceCSR, e0: torch.Tensor, n_layers: int, sum_readout: bool = False) -> torch.Tensor:
+    e0 = _check_dense(e0, a.shape[1], "E0")
+    n, d = e0.shape
+    out = torch.empty_like(e0)
+    if n_layers == 0:
+        return e0.clone()
+    layers = torch.empty((max(n_layers - 1, 1), n, d), dtype=torch.float32, device=e0.device) if n_layers > 1 else None
+    ws, ws_bytes = _ws(a, d)
+    _lib.check(_lib.lib().hgr_lightgcn_forward_f32(C.byref(a.desc), e0.data_ptr(), _lib.ptr(layers), out.data_ptr(), n_layers, d,
+                                                   int(sum_readout), ws, ws_bytes, _lib.stream_ptr()))
+    return out
+
+
+class _LightGCN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e0, a, n_layers, sum_readout):
+        ctx.a, ctx.n_layers, ctx.sum_readout = a, n_layers, sum_readout
+        return lightgcn_propagate_raw(a, e0, n_layers, sum_readout)
+
+    @staticmethod
+    def backward(ctx, dout):
+        # out = c * sum_k A^k e0  =>  de0 = c * sum_k (A^T)^k dout : the same fused call on A^T
+        return lightgcn_propagate_raw(ctx.a.t(), dout.contiguous(), ctx.n_layers, ctx.sum_readout), None, None, None
+
+
+def lightgcn_propagate(adj: DeviceCSR, ego: torch.Tensor, n_layers: int, sum_readout: bool = False) -> torch.Tensor:
+    """``mean_k (adj^k @ ego)`` for k = 0..n_layers (``sum_readout``: the plain sum) -- the body of
+    ``LGCN_Encoder.forward`` in ``n_layers`` launches; E^L and the stacked [N, L+1, D] tensor of the
+    reference are never materialised."""
+    return _LightGCN.apply(ego, adj, n_layers, sum_readout)

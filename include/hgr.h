@@ -1,0 +1,126 @@
+/*
+ * hgr.h -- C ABI of libhgr.so: the B200 (sm_100a) embedding-propagation / loss / full-rank-eval
+ * path of the SELFRec-based hypergraph-diffusion recommender.
+ *
+ * The reference (DanbiAubrey/Hypergraph_diffusion_for_recommendation) is pure Python and has no FFI;
+ * each entry point below names the reference call site (file:line, relative to HD_SELFRec/) whose
+ * library call it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add at each of those call sites.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative hgr_status; hgr_last_error() returns a
+ *     thread-local message for the last failure.  Nothing falls back to the CPU.
+ *   - all pointers are DEVICE pointers owned by the caller unless a parameter says "host"; the
+ *     library never allocates, frees or retains them (workspace comes from the caller, sized by the
+ *     *_workspace_bytes queries).  No hidden cudaMalloc, no hidden synchronisation: every call
+ *     only enqueues work on `stream` unless documented otherwise.
+ *   - dense operands are fp32, row-major, contiguous [rows, D] with D in {32, 64, 128} and 16-byte
+ *     aligned base pointers; indices are int32 (N < 2^31), nonzero offsets int64.
+ */
+#ifndef HGR_H_
+#define HGR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *hgr_stream_t; /* a cudaStream_t */
+
+typedef enum {
+    HGR_OK = 0,
+    HGR_ERR_INVALID = -1,   /* bad argument (shape, dtype width, alignment, null pointer) */
+    HGR_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed */
+    HGR_ERR_UNSUPPORTED = -3,
+    HGR_ERR_WORKSPACE = -4  /* caller-provided workspace too small */
+} hgr_status;
+
+const char *hgr_last_error(void);
+int hgr_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t hgr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse matrix in CSR with an optional split plan for long rows.
+ * Replaces the torch sparse COO tensor built by TorchGraphInterface.convert_sparse_mat_to_tensor
+ * (base/torch_interface.py:8-12).  Rows longer than `chunk_nnz` nonzeros are listed in
+ * `heavy_rows`; heavy row h owns chunks [heavy_chunk_ptr[h], heavy_chunk_ptr[h+1]) of `chunk_nnz`
+ * consecutive nonzeros each, `chunk_owner[c]` is the h of chunk c.  n_heavy_rows == 0 disables
+ * splitting (every row is then accumulated strictly sequentially, the order of the CPU oracle).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_rows, n_cols;
+    int64_t nnz;
+    const int64_t *indptr;  /* [n_rows + 1] */
+    const int32_t *indices; /* [nnz] column ids, ascending inside a row */
+    const float *values;    /* [nnz] */
+    int32_t chunk_nnz;
+    int32_t n_heavy_rows;
+    int64_t n_chunks;
+    const int32_t *heavy_rows;      /* [n_heavy_rows] */
+    const int64_t *heavy_chunk_ptr; /* [n_heavy_rows + 1] */
+    const int32_t *chunk_owner;     /* [n_chunks] */
+} hgr_csr_t;
+
+/* Row-wise epilogue fused into the propagation kernel; applied to the accumulated row `acc` in
+ * this order (every stage optional):
+ *   pre[row]  = acc                                   (saved for the backward pass)
+ *   acc       = leaky_relu(acc, slope)                HGCNConv act, model/graph/HGNN_HD3.py:545-549
+ *   acc       = LayerNorm(acc) * gamma + beta         lns[k](...), HGNN_HD3.py:421,710,714
+ *   acc      += residual[row]                         "+ res" / "+ Xve", same lines
+ *   acc       = (acc + sum_j addend[j][row]) * scale  layer mean/sum readout, LightGCN.py:135-136
+ *   y[row]    = acc
+ */
+#define HGR_MAX_ADDENDS 8
+typedef struct {
+    int32_t use_leaky;
+    float leaky_slope;
+    const float *ln_gamma; /* [D] or NULL: no LayerNorm */
+    const float *ln_beta;  /* [D] */
+    float ln_eps;
+    const float *residual; /* [n_rows, D] or NULL */
+    int32_t n_addends;
+    const float *addends[HGR_MAX_ADDENDS]; /* each [n_rows, D] */
+    float scale;                           /* applied only when n_addends > 0 or scale_always != 0 */
+    int32_t scale_always;
+    float *pre;                            /* [n_rows, D] or NULL */
+} hgr_epilogue_t;
+
+/* Y[n_rows, D] = epilogue(A . X[n_cols, D]).  Replaces torch.sparse.mm(adj, X)
+ * (model/graph/LightGCN.py:133, HCCF.py:199, SGL.py:156-160, HGNN_HD3.py:549-553).
+ * `workspace` must hold hgr_spmm_workspace_bytes(A, D) bytes (0 when the plan has no heavy rows).
+ * `epi` may be NULL.  Deterministic: the same inputs give the same bits on every run. */
+size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D);
+int hgr_spmm_f32(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi,
+                 void *workspace, size_t workspace_bytes, hgr_stream_t stream);
+
+/* Y = epilogue(A . (At . X)): the node -> hyperedge -> node two-stage propagation of
+ * HGCNConv.forward (model/graph/HGNN_HD3.py:540-553; 17 more copies listed in SURVEY.md 2.1).
+ * `At` is the CSR of A^T (pass A itself for the symmetric normalised adjacency); `tmp` is the
+ * [At->n_rows, D] hyperedge intermediate.  Workspace = max of the two stages. */
+int hgr_hgconv_f32(const hgr_csr_t *A, const hgr_csr_t *At, const float *X, float *tmp, float *Y, int32_t D,
+                   const hgr_epilogue_t *epi, void *workspace, size_t workspace_bytes, hgr_stream_t stream);
+
+/* LGCN_Encoder.forward (model/graph/LightGCN.py:129-140): E^{k+1} = A E^k for k < n_layers and
+ * out = mean_k E^k (sum_readout != 0: plain sum, the HCCF/SHT readout, HCCF.py:188).  `layers`
+ * holds the n_layers-1 intermediate tables E^1..E^{L-1} back to back ([L-1, N, D]); the last
+ * propagation never materialises E^L: its epilogue adds E^0..E^{L-1} and scales. */
+int hgr_lightgcn_forward_f32(const hgr_csr_t *A, const float *E0, float *layers, float *out, int32_t n_layers,
+                             int32_t D, int32_t sum_readout, void *workspace, size_t workspace_bytes,
+                             hgr_stream_t stream);
+
+/* Backward of y = LayerNorm(leaky_relu(pre)) * gamma + beta (the fused epilogue above, residual
+ * excluded): dpre from dy.  dgamma/dbeta are accumulated per block into `partials`
+ * ([hgr_ln_bwd_partial_rows(n_rows), 2, D]) and reduced in a fixed order by the second kernel, so
+ * the result is deterministic.  gamma == NULL means "no LayerNorm" (only the leaky slope applies). */
+int32_t hgr_ln_bwd_partial_rows(int64_t n_rows);
+int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
+                         float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
+                         float *partials, hgr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGR_H_ */

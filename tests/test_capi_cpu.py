@@ -1,0 +1,111 @@
+"""CPU-side checks of the C-ABI boundary: libhgr.so loads without a GPU, exports every symbol
+include/hgr.h declares, the ctypes mirrors have the C layout, argument validation rejects bad calls
+before touching CUDA, and the host-side split plan is right.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hgr.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hypergraph_diffusion_for_recommendation_b200 import _lib, build
+
+    build.build()  # nvcc cross-compiles for sm_100a without a GPU
+    return _lib
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hgr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 9
+    for name in names:
+        assert hasattr(handle, name), "libhgr.so does not export %s" % name
+        assert name in lib.SIGNATURES, "no ctypes signature for %s" % name
+    assert handle.hgr_version() >= 100
+    assert handle.hgr_launch_count() == 0
+
+
+def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hgr.h"\nint main(void){\n'
+                   'printf("%zu %zu %zu %zu %zu\\n", sizeof(hgr_csr_t), offsetof(hgr_csr_t, chunk_nnz), offsetof(hgr_csr_t, chunk_owner),'
+                   ' offsetof(hgr_csr_t, indptr), offsetof(hgr_csr_t, n_chunks));\n'
+                   'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(hgr_epilogue_t), offsetof(hgr_epilogue_t, ln_gamma), offsetof(hgr_epilogue_t, residual),'
+                   ' offsetof(hgr_epilogue_t, addends), offsetof(hgr_epilogue_t, scale), offsetof(hgr_epilogue_t, pre));\nreturn 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    a = [int(v) for v in out[0].split()]
+    b = [int(v) for v in out[1].split()]
+    d, e = lib.CsrDesc, lib.Epilogue
+    assert a == [C.sizeof(d), d.chunk_nnz.offset, d.chunk_owner.offset, d.indptr.offset, d.n_chunks.offset]
+    assert b == [C.sizeof(e), e.ln_gamma.offset, e.residual.offset, e.addends.offset, e.scale.offset, e.pre.offset]
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    handle = lib.lib()
+    d = lib.CsrDesc()
+    d.n_rows, d.n_cols, d.nnz = 4, 4, 0
+    dummy = (C.c_int64 * 5)()
+    d.indptr = C.addressof(dummy)
+    rc = handle.hgr_spmm_f32(C.byref(d), 16, 16, 48, None, None, 0, None)
+    assert rc == -1 and b"unsupported" in handle.hgr_last_error()
+    rc = handle.hgr_spmm_f32(C.byref(d), 8, 16, 64, None, None, 0, None)  # misaligned X
+    assert rc == -1 and b"aligned" in handle.hgr_last_error()
+    rc = handle.hgr_spmm_f32(None, 16, 16, 64, None, None, 0, None)
+    assert rc == -1
+    d.n_heavy_rows, d.chunk_nnz, d.n_chunks = 1, 8, 2
+    d.heavy_rows = d.heavy_chunk_ptr = d.chunk_owner = C.addressof(dummy)
+    rc = handle.hgr_spmm_f32(C.byref(d), 16, 16, 64, None, None, 0, None)
+    assert rc == -4 and b"workspace" in handle.hgr_last_error()
+    assert handle.hgr_spmm_workspace_bytes(C.byref(d), 64) == 2 * 64 * 4
+    with pytest.raises(lib.HgrError):
+        lib.check(rc)
+
+
+def test_split_plan_and_chunk_size():
+    from hypergraph_diffusion_for_recommendation_b200.graph import default_chunk_nnz, split_plan
+
+    indptr = np.array([0, 3, 3, 40, 41, 141], dtype=np.int64)
+    heavy, ptr, owner = split_plan(indptr, 16)
+    assert list(heavy) == [2, 4]
+    assert list(ptr) == [0, 3, 10]  # ceil(37/16) = 3, ceil(100/16) = 7
+    assert list(owner) == [0] * 3 + [1] * 7
+    heavy, ptr, owner = split_plan(indptr, 1000)
+    assert heavy.size == 0 and list(ptr) == [0] and owner.size == 0
+    assert default_chunk_nnz(2_000_000_000) == 1024 and default_chunk_nnz(140_000) == 64
+    assert default_chunk_nnz(6_000_000) == 256
+
+
+def test_product_package_never_imports_the_oracle():
+    """A product path that routes through oracle/ would void every parity claim."""
+    pkg = os.path.join(ROOT, "hypergraph_diffusion_for_recommendation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "libhgr_oracle" not in text, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from hypergraph_diffusion_for_recommendation_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhgr.so")
+    with pytest.raises(_lib.HgrError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

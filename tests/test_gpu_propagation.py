@@ -1,0 +1,248 @@
+"""GPU parity of the propagation path (libhgr.so through the C ABI) against the oracle and the
+reference-generated golden vectors.  Bit-exact where a row is accumulated sequentially; 1e-5
+relative (north_star) everywhere else, tolerance written at each assert."""
+import types
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import hgr_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def rel_err(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), 1e-30)
+
+
+def bits(a):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def params(golden, prefix):
+    return {k[len(prefix):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith(prefix)}
+
+
+@pytest.fixture(scope="module")
+def hgr():
+    import hypergraph_diffusion_for_recommendation_b200 as pkg
+    from hypergraph_diffusion_for_recommendation_b200 import _lib, encoders, graph, ops
+
+    assert torch.cuda.is_available()
+    _lib.lib()  # raises if libhgr.so is missing: there is no fallback
+    return types.SimpleNamespace(pkg=pkg, lib=_lib, enc=encoders, graph=graph, ops=ops)
+
+
+@pytest.fixture(scope="module")
+def adj(hgr, pl_graph):
+    n = pl_graph["n_users"] + pl_graph["n_items"]
+    return hgr.graph.DeviceCSR.from_host(*pl_graph["csr"], (n, n), symmetric=True, chunk_nnz=1 << 20)
+
+
+@pytest.fixture(scope="module")
+def data(pl_graph):
+    n = pl_graph["n_users"] + pl_graph["n_items"]
+    ip, ix, dv = pl_graph["csr"]
+    return types.SimpleNamespace(n_users=pl_graph["n_users"], n_items=pl_graph["n_items"],
+                                 norm_adj=sp.csr_matrix((dv, ix, ip), shape=(n, n)))
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------ SpMM
+def test_spmm_bit_exact_vs_oracle_and_reference(hgr, golden, pl_graph, adj):
+    y = hgr.ops.spmm_raw(adj, cuda(golden["spmm_X"]))
+    assert np.array_equal(bits(y), bits(O.spmm(*pl_graph["csr"], golden["spmm_X"])))
+    assert np.array_equal(bits(y), bits(golden["spmm_Y"]))  # torch.sparse.mm on CPU, same bits
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_spmm_widths_and_split_rows(hgr, pl_graph, d):
+    n = pl_graph["n_users"] + pl_graph["n_items"]
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ref = O.spmm(*pl_graph["csr"], x)
+    whole = hgr.graph.DeviceCSR.from_host(*pl_graph["csr"], (n, n), symmetric=True, chunk_nnz=1 << 20)
+    assert whole.desc.n_heavy_rows == 0
+    assert np.array_equal(bits(hgr.ops.spmm_raw(whole, cuda(x))), bits(ref))
+    split = hgr.graph.DeviceCSR.from_host(*pl_graph["csr"], (n, n), symmetric=True, chunk_nnz=8)
+    assert split.desc.n_heavy_rows > 0
+    y1, y2 = hgr.ops.spmm_raw(split, cuda(x)), hgr.ops.spmm_raw(split, cuda(x))
+    assert np.array_equal(bits(y1), bits(y2))  # deterministic: no atomics
+    assert rel_err(y1, ref) < RTOL
+    light = np.diff(pl_graph["csr"][0]) <= 8
+    assert np.array_equal(bits(y1)[light], bits(ref)[light])  # unsplit rows stay bit-exact
+
+
+def test_spmm_empty_rows_and_empty_matrix(hgr):
+    indptr = np.array([0, 0, 2, 2, 3, 3], dtype=np.int64)
+    indices = np.array([4, 0, 1], dtype=np.int32)
+    vals = np.array([0.5, -2.0, 3.0], dtype=np.float32)
+    a = hgr.graph.DeviceCSR.from_host(indptr, indices, vals, (5, 5))
+    x = np.arange(5 * 32, dtype=np.float32).reshape(5, 32)
+    y = hgr.ops.spmm_raw(a, cuda(x)).cpu().numpy()
+    assert np.array_equal(y, O.spmm(indptr, indices, vals, x))
+    assert not y[[0, 2, 4]].any()
+    e = hgr.graph.DeviceCSR.from_host(np.zeros(4, dtype=np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), (3, 7))
+    assert not hgr.ops.spmm_raw(e, torch.ones(7, 64, device="cuda")).any()
+    with pytest.raises(ValueError):
+        hgr.ops.spmm_raw(a, torch.ones(5, 48, device="cuda"))  # unsupported width fails loudly
+    with pytest.raises(hgr.lib.HgrError):
+        hgr.ops.spmm_raw(a, torch.ones(5, 64))  # CPU tensor: no fallback
+
+
+def test_spmm_epilogue_stages(hgr, pl_graph, adj):
+    n = pl_graph["n_users"] + pl_graph["n_items"]
+    rng = np.random.default_rng(3)
+    x, res, a0, a1 = (rng.standard_normal((n, 64)).astype(np.float32) for _ in range(4))
+    gamma, beta = rng.standard_normal(64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    z = O.spmm(*pl_graph["csr"], x)
+    pre = torch.empty(n, 64, device="cuda")
+    ep = hgr.ops._epilogue(slope=0.3, gamma=cuda(gamma), beta=cuda(beta), residual=cuda(res), addends=(cuda(a0), cuda(a1)),
+                           scale=0.25, pre=pre)
+    keep = (ep,)  # the descriptor only borrows the tensors
+    y = hgr.ops.spmm_raw(adj, cuda(x), ep)
+    want = (O.layer_norm(O.leaky_relu(z, 0.3), gamma, beta) + res + (a0 + a1)) * np.float32(0.25)
+    assert np.array_equal(bits(pre), bits(z))
+    assert rel_err(y, want) < RTOL
+    del keep
+
+
+def test_spmm_properties_on_a_larger_graph(hgr):
+    """Size-independent checks at a size the oracle still finishes quickly: A 1 = rowsum,
+    linearity, and <y, A x> = <A y, x> for the symmetric adjacency."""
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions
+
+    g = powerlaw_interactions(3000, 5000, 120_000, seed=3)
+    csr = O.build_norm_adj(g.train_u, g.train_i, 3000, 5000)
+    a = hgr.graph.DeviceCSR.from_host(*csr, (8000, 8000), symmetric=True)
+    assert a.desc.n_heavy_rows > 0  # the default plan splits the popular items
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((8000, 64)).astype(np.float32)
+    z = rng.standard_normal((8000, 64)).astype(np.float32)
+    y = hgr.ops.spmm_raw(a, cuda(x))
+    assert rel_err(y, O.spmm(*csr, x)) < RTOL
+    ones = hgr.ops.spmm_raw(a, torch.ones(8000, 64, device="cuda"))
+    rowsum = np.add.reduceat(csr[2].astype(np.float64), csr[0][:-1])
+    assert rel_err(ones[:, 0], rowsum) < RTOL
+    lin = hgr.ops.spmm_raw(a, cuda(2 * x - 3 * z))
+    assert rel_err(lin, 2 * y.cpu().numpy() - 3 * hgr.ops.spmm_raw(a, cuda(z)).cpu().numpy()) < 1e-4
+    yz = hgr.ops.spmm_raw(a, cuda(z))
+    lhs = float((cuda(z).double() * y.double()).sum())
+    rhs = float((yz.double() * cuda(x).double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+
+
+# ------------------------------------------------------------------------------------------ autograd ops
+def test_spmm_backward_matches_reference_autograd(hgr, golden, adj):
+    x = cuda(golden["spmm_X"]).requires_grad_(True)
+    y = hgr.ops.spmm(adj, x)
+    (y * cuda(golden["spmm_G"])).sum().backward()
+    assert rel_err(x.grad, golden["spmm_dX"]) < RTOL
+
+
+def test_hgconv_forward_backward(hgr, golden, adj):
+    x = cuda(golden["hgconv_X"]).requires_grad_(True)
+    y = hgr.ops.hgconv(adj, x, slope=0.5)
+    assert rel_err(y, golden["hgconv_Y_act"]) < RTOL
+    (y * cuda(golden["spmm_G"])).sum().backward()
+    assert rel_err(x.grad, golden["hgconv_dX_act"]) < RTOL
+    with torch.no_grad():
+        y0 = hgr.ops.hgconv(adj, x, slope=None)
+    assert np.array_equal(bits(y0), bits(golden["hgconv_Y_noact"]))  # symmetric A, sequential rows: same bits as torch CPU
+
+
+def test_hgconv_asymmetric_after_edge_drop(hgr, golden, adj):
+    dropped = hgr.enc.SpAdjDropEdge()(adj, float(golden["drop_keep"]), rand=torch.from_numpy(golden["drop_rand"]))
+    ip, ix, dv = dropped.to_host()
+    rows = np.repeat(np.arange(ip.size - 1), np.diff(ip))
+    assert np.array_equal(np.stack([rows, ix]), golden["drop_indices"])
+    assert np.array_equal(bits(dv), bits(golden["drop_values"]))
+    x = cuda(golden["drop_X"])
+    assert np.array_equal(bits(hgr.ops.spmm_raw(dropped, x)), bits(golden["drop_Y"]))
+    y = hgr.enc.HGCNConv(0.3)(dropped, x, act=True)
+    assert rel_err(y, golden["drop_hgconv_Y"]) < RTOL
+    # transpose handle: (A^T)^T round trip and A^T x against the oracle
+    tip, tix, tdv = O.csr_transpose(ip.astype(np.int64), ix.astype(np.int64), dv, dropped.shape[1])
+    t = dropped.t()
+    assert np.array_equal(t.to_host()[0], tip) and np.array_equal(t.to_host()[1], tix) and np.array_equal(bits(t.to_host()[2]), bits(tdv))
+
+
+def test_lightgcn_propagate_and_backward(hgr, golden, adj, pl_graph):
+    e0 = cuda(np.concatenate([golden["lgcn_user_emb0"], golden["lgcn_item_emb0"]], 0)).requires_grad_(True)
+    out = hgr.ops.lightgcn_propagate(adj, e0, 3)
+    u = pl_graph["n_users"]
+    assert rel_err(out[:u], golden["lgcn_user_out"]) < RTOL and rel_err(out[u:], golden["lgcn_item_out"]) < RTOL
+    g = cuda(golden["spmm_G"])
+    (out * g).sum().backward()
+    # d/dE0 of mean_k A^k E0 contracted with G is mean_k A^k G (A symmetric)
+    want = O.lgcn_forward(pl_graph["csr"], golden["spmm_G"][:u], golden["spmm_G"][u:], 3)
+    assert rel_err(e0.grad, np.concatenate(want, 0)) < RTOL
+    s = hgr.ops.lightgcn_propagate(adj, e0.detach(), 2, sum_readout=True)
+    e = e0.detach().cpu().numpy()
+    e1 = O.spmm(*pl_graph["csr"], e)
+    assert rel_err(s, e + e1 + O.spmm(*pl_graph["csr"], e1)) < RTOL
+
+
+# ------------------------------------------------------------------------------------------ encoders
+def test_lgcn_encoder_matches_reference(hgr, golden, data):
+    enc = hgr.enc.LGCN_Encoder(data, 64, 3)
+    enc.load_state_dict({"embedding_dict.user_emb": torch.from_numpy(golden["lgcn_user_emb0"]),
+                         "embedding_dict.item_emb": torch.from_numpy(golden["lgcn_item_emb0"])}, strict=True)
+    enc = enc.cuda()
+    with torch.no_grad():
+        ue, ie = enc()
+    assert rel_err(ue, golden["lgcn_user_out"]) < RTOL and rel_err(ie, golden["lgcn_item_out"]) < RTOL
+
+
+def test_equiv_set_conv_matches_reference(hgr, golden, data, adj):
+    esc = hgr.enc.EquivSetConv(64, 64, data.n_users, data.n_items, mlp1_layers=0, mlp2_layers=0, mlp3_layers=1, alpha=0.0,
+                               aggr="mean", dropout=0.5, normalization="ln", input_norm=True, data=data)
+    esc.load_state_dict(params(golden, "esc_param/"), strict=True)  # same state_dict keys as the reference module
+    esc = esc.cuda().eval()
+    x = cuda(golden["esc_X"]).requires_grad_(True)
+    y = esc(x, adj, x, None)
+    assert rel_err(y, golden["esc_Y"]) < RTOL
+    (y * cuda(golden["spmm_G"])).sum().backward()
+    assert rel_err(x.grad, golden["esc_dX"]) < 2e-5
+    for k, p in esc.named_parameters():
+        assert rel_err(p.grad, golden["esc_grad/" + k]) < 2e-5, k
+
+
+def test_local_aware_encoder_matches_reference(hgr, golden, data, adj):
+    lae = hgr.enc.LocalAwareEncoder(data, 64, 64, 2, 0.3, 0.2)
+    lae.load_state_dict(params(golden, "lae_param/"), strict=True)
+    lae = lae.cuda().eval()
+    e0 = cuda(golden["lae_E0"]).requires_grad_(True)
+    lu, li = lae(e0, lae.sparse_norm_adj)
+    assert rel_err(lu, golden["lae_user_out"]) < RTOL and rel_err(li, golden["lae_item_out"]) < RTOL
+    (torch.cat([lu, li], 0) * cuda(golden["spmm_G"])).sum().backward()
+    assert rel_err(e0.grad, golden["lae_dE0"]) < 2e-5
+    checked = 0
+    for k, p in lae.named_parameters():
+        if "lae_grad/" + k in golden.files:
+            assert rel_err(p.grad, golden["lae_grad/" + k]) < 5e-5, k
+            checked += 1
+    assert checked >= 10
+
+
+def test_hccf_encoder_matches_reference(hgr, golden, data):
+    conf = dict(lrate=0.001, lr_decay=0.9, max_epoch=1, batch_size=64, reg=0.1, embedding_size=64, hyper_dim=32, drop_rate=0.5,
+                p=0.1, n_layers=2)
+    hc = hgr.enc.HCCFEncoder(conf, data)
+    hc.load_state_dict(params(golden, "hccf_param/"), strict=True)
+    hc = hc.cuda().eval()
+    with torch.no_grad():
+        hu, hi, gcn_h, hyp_h = hc(keep_rate=1.0)
+    assert rel_err(hu, golden["hccf_user_out"]) < RTOL and rel_err(hi, golden["hccf_item_out"]) < RTOL
+    for l in range(2):
+        assert rel_err(gcn_h[l], golden["hccf_gcn_%d" % l]) < RTOL
+        assert rel_err(hyp_h[l], golden["hccf_hyp_%d" % l]) < 1e-4  # dense fp32 GEMM (cuBLAS may use a different order)
