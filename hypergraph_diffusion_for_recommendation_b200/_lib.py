@@ -45,11 +45,20 @@ SIGNATURES = {
     "hgr_version": (C.c_int, []),
     "hgr_launch_count": (C.c_uint64, []),
     "hgr_spmm_workspace_bytes": (_SZ, [C.POINTER(CsrDesc), _I32]),
+    "hgr_set_spmm_variant": (C.c_int, [C.c_int]),
     "hgr_spmm_f32": (C.c_int, [C.POINTER(CsrDesc), _VP, _VP, _I32, C.POINTER(Epilogue), _VP, _SZ, _VP]),
     "hgr_hgconv_f32": (C.c_int, [C.POINTER(CsrDesc), C.POINTER(CsrDesc), _VP, _VP, _VP, _I32, C.POINTER(Epilogue), _VP, _SZ, _VP]),
     "hgr_lightgcn_forward_f32": (C.c_int, [C.POINTER(CsrDesc), _VP, _VP, _VP, _I32, _I32, _I32, _VP, _SZ, _VP]),
     "hgr_ln_bwd_partial_rows": (_I32, [_I64]),
     "hgr_leaky_ln_bwd_f32": (C.c_int, [_VP, _VP, _VP, _F32, _I32, _F32, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "hgr_build_csr_workspace_bytes": (_SZ, [_I64]),
+    "hgr_coo_to_csr": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "hgr_bipartite_to_csr": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "hgr_degree_scale": (C.c_int, [_VP, _I64, _VP, _I32, _VP, _VP, _VP]),
+    "hgr_csr_scale": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    "hgr_bpr_l2_workspace_bytes": (_SZ, [_I64]),
+    "hgr_bpr_l2_fwd_f32": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, _VP, _VP, _I64, _F32, _F32, _VP, _VP, _SZ, _VP, _VP]),
+    "hgr_bpr_l2_bwd_f32": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, _VP, _VP, _I64, _F32, _F32, _VP, _VP, _VP, _VP, _VP]),
 }
 
 

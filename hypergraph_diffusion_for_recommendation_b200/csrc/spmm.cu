@@ -24,9 +24,12 @@
 namespace hgr {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 8;
+constexpr int kUnroll = 8;  // partial-row reduce kernel
 
-template <int LPR>
+// Tuning variant (unroll depth of the gather batch x resident blocks per SM); see hgr_set_spmm_variant.
+static int g_variant = 0;
+
+template <int LPR, int UNR>
 __device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ idx, const float *__restrict__ val,
                                                     const float4 *__restrict__ X4, int64_t s, int64_t e, int gl,
                                                     unsigned gmask) {
@@ -48,18 +51,18 @@ __device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ 
         }
         const int cnt = (int)(e - base < (int64_t)LPR ? e - base : (int64_t)LPR);
 #pragma unroll
-        for (int k0 = 0; k0 < LPR; k0 += kUnroll) {
+        for (int k0 = 0; k0 < LPR; k0 += UNR) {
             if (k0 < cnt) {
-                float4 xv[kUnroll];
-                float vv[kUnroll];
+                float4 xv[UNR];
+                float vv[UNR];
 #pragma unroll
-                for (int k = 0; k < kUnroll; ++k) {
+                for (int k = 0; k < UNR; ++k) {
                     const int cc = __shfl_sync(gmask, c, k0 + k, LPR);
                     vv[k] = __shfl_sync(gmask, v, k0 + k, LPR);
                     if (k0 + k < cnt) xv[k] = ld_ro_f4(X4 + (int64_t)cc * LPR + gl);
                 }
 #pragma unroll
-                for (int k = 0; k < kUnroll; ++k) {
+                for (int k = 0; k < UNR; ++k) {
                     if (k0 + k < cnt) {
                         acc.x = fmaf(vv[k], xv[k].x, acc.x);
                         acc.y = fmaf(vv[k], xv[k].y, acc.y);
@@ -135,8 +138,8 @@ __device__ __forceinline__ void finish_row(float4 acc, int64_t row, int gl, unsi
 }
 
 // grid = [heavy chunk blocks | light row blocks]
-template <int LPR>
-__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(hgr_csr_t A, const float4 *__restrict__ X4,
+template <int LPR, int UNR, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) spmm_rows_kernel(hgr_csr_t A, const float4 *__restrict__ X4,
                                                              float *__restrict__ Y, hgr_epilogue_t ep,
                                                              float4 *__restrict__ partials, int heavy_blocks) {
     constexpr int GPB = kThreads / LPR;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) spmm_rows_kernel(hgr_csr_t A, const 
         const int64_t s = A.indptr[row] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
         const int64_t row_end = A.indptr[row + 1];
         const int64_t e = s + A.chunk_nnz < row_end ? s + A.chunk_nnz : row_end;
-        const float4 acc = gather_accumulate<LPR>(A.indices, A.values, X4, s, e, gl, gmask);
+        const float4 acc = gather_accumulate<LPR, UNR>(A.indices, A.values, X4, s, e, gl, gmask);
         partials[chunk * LPR + gl] = acc;
         return;
     }
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) spmm_rows_kernel(hgr_csr_t A, const 
     if (row >= A.n_rows) return;
     const int64_t s = A.indptr[row], e = A.indptr[row + 1];
     if (A.n_heavy_rows > 0 && e - s > (int64_t)A.chunk_nnz) return;  // summed by spmm_heavy_reduce_kernel
-    const float4 acc = gather_accumulate<LPR>(A.indices, A.values, X4, s, e, gl, gmask);
+    const float4 acc = gather_accumulate<LPR, UNR>(A.indices, A.values, X4, s, e, gl, gmask);
     finish_row<LPR>(acc, row, gl, gmask, ep, Y);
 }
 
@@ -212,7 +215,7 @@ static int check_epilogue(const hgr_epilogue_t *ep) {
     return HGR_OK;
 }
 
-template <int LPR>
+template <int LPR, int UNR, int MINB>
 static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws,
                        cudaStream_t st) {
     constexpr int GPB = kThreads / LPR;
@@ -221,8 +224,8 @@ static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_e
     const int64_t grid = heavy_blocks + light_blocks;
     if (grid == 0) return HGR_OK;
     HGR_REQUIRE(grid < (int64_t)0x7fffffff, "grid too large (%lld blocks)", (long long)grid);
-    spmm_rows_kernel<LPR><<<(unsigned)grid, kThreads, 0, st>>>(A, reinterpret_cast<const float4 *>(X), Y, ep,
-                                                               reinterpret_cast<float4 *>(ws), (int)heavy_blocks);
+    spmm_rows_kernel<LPR, UNR, MINB><<<(unsigned)grid, kThreads, 0, st>>>(A, reinterpret_cast<const float4 *>(X), Y, ep,
+                                                                          reinterpret_cast<float4 *>(ws), (int)heavy_blocks);
     HGR_LAUNCH_OK("spmm_rows_kernel");
     if (A.n_heavy_rows > 0) {
         spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, GPB), kThreads, 0, st>>>(
@@ -230,6 +233,18 @@ static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_e
         HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
     }
     return HGR_OK;
+}
+
+template <int LPR>
+static int launch_spmm_variant(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws,
+                               cudaStream_t st) {
+    switch (g_variant) {
+        case 1: return launch_spmm<LPR, 8, 4>(A, X, Y, ep, ws, st);
+        case 2: return launch_spmm<LPR, (LPR < 16 ? LPR : 16), 2>(A, X, Y, ep, ws, st);
+        case 3: return launch_spmm<LPR, 4, 6>(A, X, Y, ep, ws, st);
+        case 4: return launch_spmm<LPR, 8, 5>(A, X, Y, ep, ws, st);
+        default: return launch_spmm<LPR, 8, 3>(A, X, Y, ep, ws, st);
+    }
 }
 
 static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi, void *ws,
@@ -252,15 +267,21 @@ static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, co
         ep.scale = 1.f;
     }
     switch (D) {
-        case 32: return launch_spmm<8>(*A, X, Y, ep, ws, st);
-        case 64: return launch_spmm<16>(*A, X, Y, ep, ws, st);
-        default: return launch_spmm<32>(*A, X, Y, ep, ws, st);
+        case 32: return launch_spmm_variant<8>(*A, X, Y, ep, ws, st);
+        case 64: return launch_spmm_variant<16>(*A, X, Y, ep, ws, st);
+        default: return launch_spmm_variant<32>(*A, X, Y, ep, ws, st);
     }
 }
 
 }  // namespace hgr
 
 extern "C" {
+
+int hgr_set_spmm_variant(int variant) {
+    HGR_REQUIRE(variant >= 0 && variant <= 4, "variant %d out of range", variant);
+    hgr::g_variant = variant;
+    return HGR_OK;
+}
 
 size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D) {
     if (!A || A->n_heavy_rows <= 0) return 0;

@@ -120,7 +120,10 @@ class SpAdjDropEdge(nn.Module):
         counts = torch.bincount(rows[mask], minlength=adj.shape[0])
         indptr = torch.zeros(adj.shape[0] + 1, dtype=torch.int64, device=adj.device)
         torch.cumsum(counts, 0, out=indptr[1:])
-        return DeviceCSR(indptr, adj.indices[mask], adj.values[mask] / keepRate, adj.shape, chunk_nnz=adj.chunk_nnz)
+        # tensor / tensor is a true IEEE division (the scalar overload multiplies by a reciprocal on CUDA),
+        # which keeps the rescaled values bit-identical to the reference's CPU `vals[mask] / keepRate`
+        keep = torch.full((), float(keepRate), dtype=torch.float32, device=adj.device)
+        return DeviceCSR(indptr, adj.indices[mask], adj.values[mask] / keep, adj.shape, chunk_nnz=adj.chunk_nnz)
 
 
 class MLP(nn.Module):

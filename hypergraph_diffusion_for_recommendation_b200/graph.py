@@ -138,3 +138,102 @@ def transpose_csr(a: DeviceCSR) -> DeviceCSR:
     torch.cumsum(counts, 0, out=indptr[1:])
     return DeviceCSR(indptr, rows[order].contiguous(), a.values[order].contiguous(), (n_cols, n_rows),
                      chunk_nnz=a.chunk_nnz)
+
+
+# ------------------------------------------------------------------------------------------------
+# Device builders (csrc/graph_build.cu) -- replace the scipy / python-list path of the reference's
+# data layer: data/ui_graph.py:70-84,95-112 and data/graph.py:11-25.
+# ------------------------------------------------------------------------------------------------
+def host_pow_lut(n: int, exponent: float) -> np.ndarray:
+    """``np.power(arange(n, float32), exponent)`` with inf -> 0, computed on THIS host: the reference's
+    normalisation values are whatever numpy's (not correctly rounded) float32 pow returns here
+    (data/graph.py:15-16,21-22)."""
+    with np.errstate(divide="ignore"):
+        lut = np.power(np.arange(n, dtype=np.float32), np.float32(exponent))
+    lut[np.isinf(lut)] = 0.0
+    return lut.astype(np.float32)
+
+
+def _as_i32(x, device) -> torch.Tensor:
+    t = torch.as_tensor(x)
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def _build(kind: str, a: torch.Tensor, b: torch.Tensor, n_rows: int, n_cols: int, n_users: int = 0, n_items: int = 0):
+    import ctypes as C
+
+    dev = a.device
+    if dev.type != "cuda":
+        raise _lib.HgrError("graph construction runs on the GPU (no CPU path)")
+    n_in = int(a.numel())
+    n_sorted = 2 * n_in if kind == "bipartite" else n_in
+    lib = _lib.lib()
+    ws_bytes = int(lib.hgr_build_csr_workspace_bytes(n_sorted))
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    indptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(max(n_sorted, 1), dtype=torch.int32, device=dev)
+    values = torch.empty(max(n_sorted, 1), dtype=torch.float32, device=dev)
+    row_entries = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = _lib.stream_ptr()
+    if kind == "bipartite":
+        rc = lib.hgr_bipartite_to_csr(a.data_ptr(), b.data_ptr(), n_in, n_users, n_items, indptr.data_ptr(), indices.data_ptr(),
+                                      values.data_ptr(), row_entries.data_ptr(), nnz.data_ptr(), ws.data_ptr() + off, ws_bytes, st)
+    else:
+        rc = lib.hgr_coo_to_csr(a.data_ptr(), b.data_ptr(), n_in, n_rows, n_cols, indptr.data_ptr(), indices.data_ptr(),
+                                values.data_ptr(), row_entries.data_ptr(), nnz.data_ptr(), ws.data_ptr() + off, ws_bytes, st)
+    _lib.check(rc)
+    n = int(nnz.item())  # the one synchronisation of the build: the output size
+    del ws
+    return indptr, indices[:n].clone(), values[:n].clone(), row_entries[:n_rows]
+
+
+def _scale(indptr, indices, values, n_rows, row_scale, col_scale):
+    _lib.check(_lib.lib().hgr_csr_scale(indptr.data_ptr(), indices.data_ptr(), values.data_ptr(), n_rows, _lib.ptr(row_scale),
+                                        _lib.ptr(col_scale), _lib.stream_ptr()))
+
+
+def _degree_scale(deg: torch.Tensor, exponent: float) -> torch.Tensor:
+    max_deg = int(deg.max().item()) if deg.numel() else 0
+    lut = torch.from_numpy(host_pow_lut(max_deg + 1, exponent)).to(deg.device)
+    out = torch.empty(deg.numel(), dtype=torch.float32, device=deg.device)
+    over = torch.zeros(1, dtype=torch.int32, device=deg.device)
+    _lib.check(_lib.lib().hgr_degree_scale(deg.data_ptr(), deg.numel(), lut.data_ptr(), lut.numel(), out.data_ptr(), over.data_ptr(),
+                                           _lib.stream_ptr()))
+    if int(over.item()) != 0:
+        raise _lib.HgrError("degree outside the normalisation table")
+    return out
+
+
+def build_norm_adj(user_idx, item_idx, n_users: int, n_items: int, device="cuda", chunk_nnz=None, normalize: bool = True) -> DeviceCSR:
+    """``Interaction.norm_adj`` built on the device: the (U+I)^2 bipartite adjacency of the dense
+    interaction list (duplicates summed) with ``(D^-1/2 A) D^-1/2`` values, bit-identical to
+    ``Graph.normalize_graph_mat(Interaction.ui_adj)`` (data/graph.py:11-19).  ``normalize=False`` returns
+    ``ui_adj`` itself (data/ui_graph.py:70-84)."""
+    dev = torch.device(device)
+    u, i = _as_i32(user_idx, dev), _as_i32(item_idx, dev)
+    n = n_users + n_items
+    indptr, indices, values, deg = _build("bipartite", u, i, n, n, n_users, n_items)
+    if normalize:
+        d = _degree_scale(deg, -0.5)
+        _scale(indptr, indices, values, n, d, d)
+    out = DeviceCSR(indptr, indices, values, (n, n), symmetric=True, chunk_nnz=chunk_nnz)
+    out.degree = deg
+    return out
+
+
+def build_interaction_csr(user_idx, item_idx, n_users: int, n_items: int, device="cuda", transpose: bool = False,
+                          row_normalize: bool = False, chunk_nnz=None) -> DeviceCSR:
+    """``Interaction.interaction_mat`` (``transpose``: ``inv_interaction_mat``), data/ui_graph.py:95-112;
+    ``row_normalize`` applies the rectangular branch ``D^-1 R`` of ``normalize_graph_mat`` (data/graph.py:20-24).
+    Also the training-item mask of full-ranking evaluation (user -> sorted train items)."""
+    dev = torch.device(device)
+    u, i = _as_i32(user_idx, dev), _as_i32(item_idx, dev)
+    (r, c, nr, nc) = (i, u, n_items, n_users) if transpose else (u, i, n_users, n_items)
+    indptr, indices, values, deg = _build("coo", r, c, nr, nc)
+    if row_normalize:
+        _scale(indptr, indices, values, nr, _degree_scale(deg, -1.0), None)
+    out = DeviceCSR(indptr, indices, values, (nr, nc), chunk_nnz=chunk_nnz)
+    out.degree = deg
+    return out

@@ -1,0 +1,76 @@
+"""Losses of the reference's ``util/loss_torch.py`` on libhgr.so.
+
+``bpr_l2_from_tables`` is the fused product path: gathers + BPR + L2 in one forward launch and one
+backward launch (reference: ``rec_user_emb[user_idx]`` ... ``bpr_loss`` ... ``l2_reg_loss / batch_size``,
+model/graph/LightGCN.py:52-55).  ``bpr_loss`` / ``l2_reg_loss`` keep the reference signatures
+(util/loss_torch.py:5-9,17-21) for callers that already hold gathered rows.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _idx(t: torch.Tensor, device) -> torch.Tensor:
+    # the reference's sampler yields CPU LongTensors (util/sampler.py:261-263): one H2D copy here
+    return t.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+
+
+class _BprL2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, user_tab, item_tab, u, p, n, reg, batch_size):
+        if not (user_tab.is_cuda and item_tab.is_cuda):
+            raise _lib.HgrError("embedding tables must be CUDA tensors (no CPU path)")
+        user_tab, item_tab = user_tab.contiguous(), item_tab.contiguous()
+        if user_tab.dtype != torch.float32 or item_tab.dtype != torch.float32 or user_tab.shape[1] != item_tab.shape[1]:
+            raise TypeError("tables must be float32 with equal width")
+        dev = user_tab.device
+        u, p, n = _idx(u, dev), _idx(p, dev), _idx(n, dev)
+        batch = int(u.numel())
+        if p.numel() != batch or n.numel() != batch:
+            raise ValueError("user / pos / neg index arrays differ in length")
+        lib = _lib.lib()
+        saved = torch.empty(int(lib.hgr_bpr_l2_workspace_bytes(batch)), dtype=torch.uint8, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.hgr_bpr_l2_fwd_f32(user_tab.data_ptr(), item_tab.data_ptr(), user_tab.shape[0], item_tab.shape[0],
+                                          user_tab.shape[1], u.data_ptr(), p.data_ptr(), n.data_ptr(), batch, float(reg),
+                                          float(batch_size), out.data_ptr(), saved.data_ptr(), saved.numel(), bad.data_ptr(),
+                                          _lib.stream_ptr()))
+        ctx.save_for_backward(user_tab, item_tab, u, p, n, saved)
+        ctx.reg, ctx.batch_size, ctx.bad = float(reg), float(batch_size), bad
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        user_tab, item_tab, u, p, n, saved = ctx.saved_tensors
+        du, di = torch.zeros_like(user_tab), torch.zeros_like(item_tab)
+        grad = grad.contiguous().to(torch.float32)
+        _lib.check(_lib.lib().hgr_bpr_l2_bwd_f32(user_tab.data_ptr(), item_tab.data_ptr(), user_tab.shape[0], item_tab.shape[0],
+                                                 user_tab.shape[1], u.data_ptr(), p.data_ptr(), n.data_ptr(), int(u.numel()), ctx.reg,
+                                                 ctx.batch_size, saved.data_ptr(), grad.data_ptr(), du.data_ptr(), di.data_ptr(),
+                                                 _lib.stream_ptr()))
+        return du, di, None, None, None, None, None
+
+
+def bpr_l2_from_tables(user_tab, item_tab, user_idx, pos_idx, neg_idx, reg, batch_size):
+    """Returns ``(rec_loss, reg_loss)`` as 0-d tensors; ``reg_loss`` already carries ``/ batch_size``."""
+    out = _BprL2.apply(user_tab, item_tab, user_idx, pos_idx, neg_idx, reg, batch_size)
+    return out[0], out[1]
+
+
+def bpr_loss(user_emb, pos_item_emb, neg_item_emb):
+    """util/loss_torch.py:5-9 on already gathered rows (identity gather through the fused kernel)."""
+    b = user_emb.shape[0]
+    ar = torch.arange(b, device=user_emb.device)
+    items = torch.cat([pos_item_emb, neg_item_emb], 0)
+    return _BprL2.apply(user_emb, items, ar, ar, ar + b, 0.0, 1.0)[0]
+
+
+def l2_reg_loss(reg, *args):
+    """util/loss_torch.py:17-21: ``reg * sum_k ||args[k]||_F``."""
+    emb_loss = 0
+    for emb in args:
+        emb_loss = emb_loss + torch.norm(emb, p=2)
+    return emb_loss * reg

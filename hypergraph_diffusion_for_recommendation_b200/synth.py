@@ -162,3 +162,35 @@ def powerlaw_interactions_device(n_users: int, n_items: int, n_train: int, devic
     u = torch.div(keys, n_items, rounding_mode="floor").to(torch.int32)
     i = (keys % n_items).to(torch.int32)
     return u, i
+
+
+def norm_adj_from_pairs_torch(u, i, n_users: int, n_items: int, chunk_nnz=None):
+    """D^-1/2 A D^-1/2 of the bipartite graph of UNIQUE device pairs ``(u, i)`` as a ``DeviceCSR``,
+    assembled with torch ops (sort + bincount).  Benchmark plumbing for graphs too large for the host
+    generator; the product builder is ``graph.build_norm_adj`` (csrc/graph_build.cu), which also sums
+    duplicates and takes the host's ``np.power`` lookup table for bit-exact values."""
+    import torch
+
+    from .graph import DeviceCSR
+
+    n = n_users + n_items
+    u = u.to(torch.int64)
+    i = i.to(torch.int64)
+    deg_u = torch.bincount(u, minlength=n_users)
+    deg_i = torch.bincount(i, minlength=n_items)
+    deg = torch.cat([deg_u, deg_i])
+    d = deg.to(torch.float32).rsqrt()
+    d[deg == 0] = 0
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=u.device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    # user rows: items ascending; item rows: users ascending
+    key = u * n_items + i
+    key, _ = torch.sort(key)
+    ru, ci = torch.div(key, n_items, rounding_mode="floor"), key % n_items
+    del key
+    key2, _ = torch.sort(i * n_users + u)
+    ri, cu = torch.div(key2, n_users, rounding_mode="floor"), key2 % n_users
+    del key2
+    indices = torch.cat([(ci + n_users).to(torch.int32), cu.to(torch.int32)])
+    values = torch.cat([d[ru] * d[ci + n_users], d[ri + n_users] * d[cu]])
+    return DeviceCSR(indptr, indices, values, (n, n), symmetric=True, chunk_nnz=chunk_nnz)

@@ -93,6 +93,9 @@ typedef struct {
  * `workspace` must hold hgr_spmm_workspace_bytes(A, D) bytes (0 when the plan has no heavy rows).
  * `epi` may be NULL.  Deterministic: the same inputs give the same bits on every run. */
 size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D);
+/* Tuning hook: gather-batch depth x resident blocks per SM of the propagation kernel
+ * (0: 8 x 3, 1: 8 x 4, 2: 16 x 2, 3: 4 x 6, 4: 8 x 5).  Results do not depend on it. */
+int hgr_set_spmm_variant(int variant);
 int hgr_spmm_f32(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi,
                  void *workspace, size_t workspace_bytes, hgr_stream_t stream);
 
@@ -119,6 +122,65 @@ int32_t hgr_ln_bwd_partial_rows(int64_t n_rows);
 int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
                          float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
                          float *partials, hgr_stream_t stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Device construction of canonical CSR matrices (columns ascending, duplicates merged).
+ * Replaces Interaction.__create_sparse_bipartite_adjacency (data/ui_graph.py:70-84),
+ * Interaction.__create_sparse_interaction_matrix (data/ui_graph.py:95-112) and
+ * Graph.normalize_graph_mat (data/graph.py:11-25).
+ *
+ * hgr_coo_to_csr: entries (rows[j], cols[j]), each of weight 1; duplicates are summed, so
+ * values[p] is the multiplicity of the p-th distinct entry (scipy's csr_matrix((ones, (r, c)))).
+ * `indices` and `values` need room for n_entries elements; the number of distinct entries is
+ * written to the DEVICE scalar *nnz_out.  row_entries[r] (optional) = entries of row r counted
+ * with duplicates = the row sum the reference normalises by.
+ * hgr_bipartite_to_csr: the (U+I) x (U+I) adjacency [[0, R], [R^T, 0]] of the interaction list
+ * (users[j], items[j]); indices/values need room for 2 * n_edges elements.
+ * Workspace: hgr_build_csr_workspace_bytes(number of entries sorted) bytes, 256-byte aligned
+ * (n_entries for hgr_coo_to_csr, 2 * n_edges for hgr_bipartite_to_csr).
+ * ------------------------------------------------------------------------------------------- */
+size_t hgr_build_csr_workspace_bytes(int64_t n_entries);
+int hgr_coo_to_csr(const int32_t *rows, const int32_t *cols, int64_t n_entries, int32_t n_rows, int32_t n_cols,
+                   int64_t *indptr, int32_t *indices, float *values, int32_t *row_entries, int64_t *nnz_out,
+                   void *workspace, size_t workspace_bytes, hgr_stream_t stream);
+int hgr_bipartite_to_csr(const int32_t *users, const int32_t *items, int64_t n_edges, int32_t n_users, int32_t n_items,
+                         int64_t *indptr, int32_t *indices, float *values, int32_t *row_entries, int64_t *nnz_out,
+                         void *workspace, size_t workspace_bytes, hgr_stream_t stream);
+
+/* out[k] = lut[degree[k]]: the host passes lut = np.power(arange(lut_len, dtype=float32), exponent)
+ * with inf -> 0 (data/graph.py:15-16), because numpy's float32 pow is not correctly rounded and the
+ * reference's values are whatever the host's numpy returns.  *overflow (device int, optional) counts
+ * degrees outside the table. */
+int hgr_degree_scale(const int32_t *degree, int64_t n, const float *lut, int32_t lut_len, float *out, int32_t *overflow,
+                     hgr_stream_t stream);
+
+/* values[p] = (row_scale[r] * values[p]) * col_scale[c], two fp32 roundings in scipy's order:
+ * d_mat_inv.dot(adj_mat).dot(d_mat_inv) (data/graph.py:18-19).  Either scale may be NULL. */
+int hgr_csr_scale(const int64_t *indptr, const int32_t *indices, float *values, int32_t n_rows, const float *row_scale,
+                  const float *col_scale, hgr_stream_t stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * BPR + L2 loss fused with the embedding gathers (util/loss_torch.py:5-9,17-21 called from
+ * model/graph/LightGCN.py:52-55, HGNN_HD3.py:339-343, HCCF.py:60).
+ *   out[0] = mean_b -log(10e-6 + sigmoid(<U[u_b], I[p_b]> - <U[u_b], I[n_b]>))
+ *   out[1] = reg * (||U[u]||_F + ||I[p]||_F + ||I[n]||_F) / batch_size_div
+ * u, p, n are int64 [batch] (the dtype of the reference's sampler, util/sampler.py:261-263).
+ * `saved` (hgr_bpr_l2_workspace_bytes(batch) bytes) carries what the backward pass needs.
+ * Out-of-range indices are skipped and counted in *bad_index_count (device int, caller zeroes it).
+ * Backward: d_user_tab / d_item_tab must be zero-filled by the caller; row gradients are
+ * accumulated with red.global.add.f32; grad_out is the DEVICE pair (d/d out[0], d/d out[1]).
+ * ------------------------------------------------------------------------------------------- */
+size_t hgr_bpr_l2_workspace_bytes(int64_t batch);
+int hgr_bpr_l2_fwd_f32(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
+                       const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg,
+                       float batch_size_div, float *out, void *saved, size_t saved_bytes, int32_t *bad_index_count,
+                       hgr_stream_t stream);
+int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
+                       const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg,
+                       float batch_size_div, const void *saved, const float *grad_out, float *d_user_tab,
+                       float *d_item_tab, hgr_stream_t stream);
 
 #ifdef __cplusplus
 }
