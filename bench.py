@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- epoch seconds of the embedding-propagation hot path on N B200s (driver contract).
+
+A "step" is one pass of the hot path over one batch: full-graph propagation through the encoder,
+fused gather + BPR + L2 loss, backward through the same kernels, Adam.  ``value`` = epoch seconds =
+ceil(E / batch) x mean step time with the batch's triples already in HBM; ``e2e`` = the same with the
+triples arriving in pinned HOST memory every step and the two loss scalars read back (the reference's
+sampler yields CPU LongTensors and its loop calls ``.item()``, model/graph/LightGCN.py:49-59).
+
+Workloads (``--workload``; SURVEY.md section 8 shapes, synthetic power-law graphs, seed 1234):
+  c5w (default)  BASELINE configs[4] weak-scaled: 1.25 M users x 0.25 M items x 125 M interactions PER GPU
+                 (N = 8 is exactly the 10 M x 2 M x 1 B graph); inputs are larger than L2, no flush needed
+  c4 / c3 / c2   the named Amazon-Book / Gowalla / ml-1m shapes on one GPU; L2 is flushed between steps
+
+``--impl reference`` times the reference's own CPU torch path (oracle/torch_path.py, the same torch
+calls the reference makes) on the host cores, on a bounded sample of the same workload, and prints
+the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (users, items, train interactions, batch, scales_with_gpus)
+    "c5w": (1_250_000, 250_000, 125_000_000, 1_048_576, True),
+    "c4": (52_000, 92_000, 3_000_000, 4096, False),
+    "c3": (30_000, 41_000, 1_000_000, 4096, False),
+    "c2": (6_040, 3_706, 750_000, 2048, False),
+}
+MODELS = {"hgnn_hd3": "HGNN_HD3 local encoder (EquivSetConv + HGCNConv), 2 layers", "lightgcn": "LightGCN, 3 layers"}
+D = 64
+REG = 0.01
+LR = 0.001
+CPU_SAMPLE_DIV = {"c5w": 64, "c4": 1, "c3": 1, "c2": 1}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5w", choices=sorted(WORKLOADS))
+    ap.add_argument("--model", default="hgnn_hd3", choices=sorted(MODELS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def spmm_algorithmic_bytes(n_rows, n_cols, nnz, d):
+    """indptr + col + val + gather + write, int64 row offsets as stored.
+    Gather = the whole X once when it is L2-resident (<= 64 MB), else one row per nonzero."""
+    x_bytes = 4 * d * n_cols
+    gather = x_bytes if x_bytes <= 64e6 else 4 * d * nnz
+    return 8 * (n_rows + 1) + 4 * nnz + 4 * nnz + gather + 4 * d * n_rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload_dims(name, n_gpus):
+    u, i, e, b, scales = WORKLOADS[name]
+    k = n_gpus if scales else 1
+    return u * k, i * k, e * k, b * k
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU torch path on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
+    import numpy as np
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions
+    from oracle import hgr_oracle as O
+    from oracle import torch_path as T
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    U, I, E, B = workload_dims(workload, n_gpus)
+    div = CPU_SAMPLE_DIV[workload] * (n_gpus if WORKLOADS[workload][4] else 1)
+    su, si, se, sb = max(U // div, 64), max(I // div, 64), max(E // div, 1024), max(B // div, 256)
+    g = powerlaw_interactions(su, si, se, seed=1234)
+    csr = O.build_norm_adj(g.train_u, g.train_i, su, si)
+    adj = T.coo_from_csr(*csr, (su + si, su + si))
+    torch.manual_seed(1234)
+    model = T.HGNNModel(adj, su, si, D, 2) if model_name == "hgnn_hd3" else T.LGCN(adj, su, si, D, 3)
+    model.eval()  # dropout off, like the GPU arm (the reference's loop leaves it off after the first batch)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    rng = np.random.default_rng(7)
+    times = []
+    for s in range(warmup + steps):
+        pick = rng.integers(0, g.train_u.size, sb)
+        u = torch.from_numpy(g.train_u[pick])
+        p = torch.from_numpy(g.train_i[pick])
+        n = torch.from_numpy(rng.integers(0, si, sb))
+        t0 = time.perf_counter()
+        T.train_step(model, opt, u, p, n, REG, sb)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    step_s = sum(times) / len(times)
+    steps_per_epoch = math.ceil(E / B)
+    # work per step is proportional to nnz: scale the sampled step back to the full graph
+    epoch_s = step_s * div * steps_per_epoch
+    sample = "%d x %d x %d interactions (1/%d of the workload), batch %d, %d threads; step time x %d x %d steps/epoch" % (
+        su, si, se, div, sb, cores, div, steps_per_epoch)
+    return {"epoch_s": epoch_s, "step_ms_sample": step_s * 1e3, "cores": cores, "sample": sample, "div": div,
+            "nnz_per_s": 2 * se * (12 if model_name == "hgnn_hd3" else 6) / step_s}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.workload, args.model, max(1, min(args.steps, 3)), min(args.warmup, 1), args.gpus)
+    U, I, E, B = workload_dims(args.workload, args.gpus)
+    line = {
+        "impl": "reference", "metric": "epoch_s", "value": r["epoch_s"], "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["step_ms_sample"] * r["div"], "higher_is_better": False,
+        "scaling": "weak" if WORKLOADS[args.workload][4] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d users x %d items x %d interactions, emb %d, %s, batch %d" % (args.workload, U, I, E, D, MODELS[args.model], B)},
+        "cpu_baseline": {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["epoch_s"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    from hypergraph_diffusion_for_recommendation_b200 import _lib, encoders, ops, trainer
+    from hypergraph_diffusion_for_recommendation_b200.synth import norm_adj_from_pairs_torch, powerlaw_interactions_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run --nproc-per-node N)" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libhgr.so has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    U, I, E, B = workload_dims(args.workload, world)
+    small = not WORKLOADS[args.workload][4]
+    u, i = powerlaw_interactions_device(U, I, E, dev, seed=1234)
+    if world > 1:
+        from hypergraph_diffusion_for_recommendation_b200 import dist as hdist
+
+        ctx = hdist.build_partitioned(u, i, U, I, rank, world, dev)
+        data, adj = ctx.data, ctx.adj
+    else:
+        adj = norm_adj_from_pairs_torch(u, i, U, I)
+        data = types.SimpleNamespace(n_users=U, n_items=I, norm_adj=None, norm_adj_device=adj)
+    nnz = int(adj._nnz())
+    torch.manual_seed(1234)
+    if args.model == "hgnn_hd3":
+        model = encoders.HGNNModel(data, {"hyper_dim": D, "n_layers": 2, "p": 0.3, "drop_rate": 0.2, "batch_size": B}).to(dev)
+    else:
+        model = encoders.LGCN_Encoder(data, D, 3).to(dev)
+    model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
+    optimizer = torch.optim.Adam(model.parameters(), lr=LR, fused=True)
+
+    # triples for every step: positives from the training list, uniform negatives (device sampler is a
+    # "next" row of SURVEY.md 8f; parity runs replay the reference sampler's triples instead)
+    n_steps = args.warmup + args.steps
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    b_local = B // world
+    host_triples, dev_triples = [], []
+    for s in range(n_steps):
+        pick = torch.randint(0, int(u.numel()), (b_local,), device=dev, generator=gen)
+        tu, tp = u[pick].to(torch.int64), i[pick].to(torch.int64)
+        tn = torch.randint(0, I, (b_local,), device=dev, generator=gen)
+        dev_triples.append((tu, tp, tn))
+        host_triples.append(tuple(t.cpu().pin_memory() for t in (tu, tp, tn)))
+    del u, i
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+
+    spmm_events = []
+    ops.PROFILE_EVENTS = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(tri):
+        return trainer.train_step(model, optimizer, tri[0], tri[1], tri[2], REG, B)
+
+    def timed(kind):
+        """K steps; returns (total ms over the timed steps as max over ranks, last losses)."""
+        losses = None
+        for s in range(args.warmup):
+            losses = step(dev_triples[s])
+            if kind == "e2e":
+                losses.tolist()
+        barrier()
+        per_step = []
+        launches0 = _lib.launch_count()
+        ops.PROFILE_EVENTS = spmm_events if kind == "device" else None
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        if not small:
+            t_start.record()
+        for s in range(args.warmup, n_steps):
+            if small:
+                flush.fill_(s & 0xff)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if kind == "e2e":
+                tri = tuple(t.to(dev, non_blocking=True) for t in host_triples[s])
+                losses = step(tri)
+                host_losses = losses.tolist()  # D2H of the step's result, like the reference's .item() calls
+            else:
+                losses = step(dev_triples[s])
+            if small:
+                e1.record()
+                per_step.append((e0, e1))
+        if not small:
+            t_end.record()
+        barrier()
+        ops.PROFILE_EVENTS = None
+        launches = _lib.launch_count() - launches0
+        total = sum(a.elapsed_time(b) for a, b in per_step) if small else t_start.elapsed_time(t_end)
+        if world > 1:
+            t = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, losses, launches
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    total_ms, losses, launches = timed("device")
+    clock_info = clocks.stop()
+    e2e_ms, _, _ = timed("e2e")
+
+    ms_per_step = total_ms / args.steps
+    steps_per_epoch = math.ceil(E / B)
+    epoch_s = ms_per_step * steps_per_epoch / 1e3
+    e2e_epoch_s = e2e_ms / args.steps * steps_per_epoch / 1e3
+
+    # roofline of the dominant kernel (spmm_rows_kernel + its partial-row reduce), timed live
+    torch.cuda.synchronize()
+    spmm_total_ms = sum(a.elapsed_time(b) for a, b, _ in spmm_events)
+    spmm_ms = [spmm_total_ms / max(sum(c for _, _, c in spmm_events), 1)] * sum(c for _, _, c in spmm_events)
+    peak, peak_src = measured_peaks()
+    n_rows, n_cols = adj.shape
+    alg = spmm_algorithmic_bytes(n_rows, n_cols, nnz, D)
+    avg_ms = sum(spmm_ms) / max(len(spmm_ms), 1)
+    achieved = alg / (avg_ms * 1e-3) / 1e9 if spmm_ms else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": None, "kernel": "spmm_rows_kernel<16,4,6> (+ spmm_heavy_reduce_kernel)", "launch_ms": avg_ms,
+                "launches_timed": len(spmm_ms), "algorithmic_bytes": alg, "peak_source": peak_src,
+                "spmm_share_of_step": sum(spmm_ms) / total_ms if spmm_ms else None,
+                "note": "algorithmic bytes charge one 256-B row per nonzero to HBM (SURVEY.md 8d); the power-law graph lets L2 absorb "
+                        "about two thirds of that, so achieved can exceed the copy peak -- see profiles/"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = cpu_reference_run(args.workload, args.model, args.cpu_steps, 1, world)
+            cpu = {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line = {
+            "metric": "epoch_s", "value": epoch_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if WORKLOADS[args.workload][4] else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d users x %d items x %d interactions, emb %d, %s, batch %d" % (args.workload, U, I, E, D, MODELS[args.model], B),
+                       "steps_per_epoch": steps_per_epoch, "nnz": nnz,
+                       "l2": "flushed between steps (256 MiB write)" if small else "inputs larger than L2 (CSR %.1f GB + tables %.2f GB)" % (nnz * 8 / 1e9, (U + I) * D * 4 / 1e9),
+                       "parallelism": "1 GPU" if world == 1 else "row-partitioned x%d, NCCL all-gather per propagation" % world},
+            "e2e": {"value": e2e_epoch_s, "unit": "s", "h2d_bytes_per_step": 3 * 8 * b_local, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+            "loss": [float(x) for x in losses.tolist()],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

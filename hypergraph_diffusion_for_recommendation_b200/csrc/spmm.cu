@@ -27,7 +27,7 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 8;  // partial-row reduce kernel
 
 // Tuning variant (unroll depth of the gather batch x resident blocks per SM); see hgr_set_spmm_variant.
-static int g_variant = 0;
+static int g_variant = 0;  // 0 = gather batch 4, 6 blocks/SM
 
 template <int LPR, int UNR>
 __device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ idx, const float *__restrict__ val,
@@ -238,12 +238,13 @@ static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_e
 template <int LPR>
 static int launch_spmm_variant(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws,
                                cudaStream_t st) {
+    // measured on B200 (profiles/spmm_variants_r1.md): resident warps beat deeper gather batches
     switch (g_variant) {
-        case 1: return launch_spmm<LPR, 8, 4>(A, X, Y, ep, ws, st);
-        case 2: return launch_spmm<LPR, (LPR < 16 ? LPR : 16), 2>(A, X, Y, ep, ws, st);
-        case 3: return launch_spmm<LPR, 4, 6>(A, X, Y, ep, ws, st);
-        case 4: return launch_spmm<LPR, 8, 5>(A, X, Y, ep, ws, st);
-        default: return launch_spmm<LPR, 8, 3>(A, X, Y, ep, ws, st);
+        case 1: return launch_spmm<LPR, 8, 3>(A, X, Y, ep, ws, st);
+        case 2: return launch_spmm<LPR, 8, 4>(A, X, Y, ep, ws, st);
+        case 3: return launch_spmm<LPR, 4, 5>(A, X, Y, ep, ws, st);
+        case 4: return launch_spmm<LPR, 2, 8>(A, X, Y, ep, ws, st);
+        default: return launch_spmm<LPR, 4, 6>(A, X, Y, ep, ws, st);
     }
 }
 

@@ -349,3 +349,38 @@ class HCCFEncoder(nn.Module):
             hidden += [gcn_emb + hgnn_hidden[-1]]
         embeddings = sum(hidden)
         return embeddings[:n_users], embeddings[n_users:], gcn_hidden, hgnn_hidden
+
+
+class HGNNModel(nn.Module):
+    """``HGNNModel`` of the hypergraph-diffusion recommender in ``--mode=local_only``
+    (model/graph/HGNN_HD3.py:248-330): the two embedding tables plus ``LocalAwareEncoder``.  The
+    group branch (``GroupAwareEncoder``: HWNN wavelet layers on dense N x N matrices) is out of scope
+    (SURVEY.md 2.3)."""
+
+    def __init__(self, data, args, device=None):
+        super(HGNNModel, self).__init__()
+        self.data = data
+        self.device = device
+        self.hyper_dim = int(args['hyper_dim'])
+        self.layers = int(args['n_layers'])
+        self.p = float(args.get('p', 0.3))
+        self.drop_rate = float(args.get('drop_rate', 0.2))
+        self.batchSize = int(args.get('batch_size', 2048))
+        self.sparse_norm_adj = _adjacency_of(data)
+        initializer = nn.init.xavier_uniform_
+        self.embedding_dict = nn.ParameterDict({
+            'user_emb': nn.Parameter(initializer(torch.empty(self.data.n_users, self.hyper_dim))),
+            'item_emb': nn.Parameter(initializer(torch.empty(self.data.n_items, self.hyper_dim))),
+        })
+        self.hgnn_layer_local = LocalAwareEncoder(self.data, self.hyper_dim, self.hyper_dim, self.layers, self.p, self.drop_rate, device)
+        self.edgeDropper = SpAdjDropEdge()
+
+    def calculate_local_embeddings(self, keep_rate: float = 1):
+        ego_embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
+        sparse_norm_adj = self.edgeDropper(self.sparse_norm_adj, keep_rate)
+        return self.hgnn_layer_local(ego_embeddings, sparse_norm_adj)
+
+    def forward(self, mode='local', keep_rate=1):
+        if mode != 'local':
+            raise NotImplementedError("only the local (hypergraph-diffusion) branch is on the B200 path")
+        return self.calculate_local_embeddings(keep_rate=keep_rate)

@@ -22,6 +22,26 @@ from .graph import DeviceCSR
 
 _SUPPORTED_D = (32, 64, 128)
 
+# bench.py sets this to a list to time the propagation calls live: every C-ABI propagation call then
+# appends (start_event, end_event, number of SpMM launches inside the call).
+PROFILE_EVENTS = None
+
+
+class _Timed:
+    def __init__(self, n_spmm):
+        self.n = n_spmm
+
+    def __enter__(self):
+        if PROFILE_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILE_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE_EVENTS.append((self.e0, e1, self.n))
+
 
 def _check_dense(x: torch.Tensor, rows: int, what: str) -> torch.Tensor:
     if not x.is_cuda:
@@ -61,8 +81,9 @@ def spmm_raw(a: DeviceCSR, x: torch.Tensor, ep: _lib.Epilogue | None = None, out
     d = x.shape[1]
     y = out if out is not None else torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
     ws, ws_bytes = _ws(a, d)
-    _lib.check(_lib.lib().hgr_spmm_f32(C.byref(a.desc), x.data_ptr(), y.data_ptr(), d, None if ep is None else C.byref(ep),
-                                       ws, ws_bytes, _lib.stream_ptr()))
+    with _Timed(1):
+        _lib.check(_lib.lib().hgr_spmm_f32(C.byref(a.desc), x.data_ptr(), y.data_ptr(), d, None if ep is None else C.byref(ep),
+                                           ws, ws_bytes, _lib.stream_ptr()))
     return y
 
 
@@ -75,8 +96,9 @@ def hgconv_raw(a: DeviceCSR, at: DeviceCSR, x: torch.Tensor, ep: _lib.Epilogue |
     w1, b1 = _ws(a, d)
     w2, b2 = _ws(at, d)
     ws, ws_bytes = (w1, b1) if b1 >= b2 else (w2, b2)
-    _lib.check(_lib.lib().hgr_hgconv_f32(C.byref(a.desc), C.byref(at.desc), x.data_ptr(), tmp.data_ptr(), y.data_ptr(), d,
-                                         None if ep is None else C.byref(ep), ws, ws_bytes, _lib.stream_ptr()))
+    with _Timed(2):
+        _lib.check(_lib.lib().hgr_hgconv_f32(C.byref(a.desc), C.byref(at.desc), x.data_ptr(), tmp.data_ptr(), y.data_ptr(), d,
+                                             None if ep is None else C.byref(ep), ws, ws_bytes, _lib.stream_ptr()))
     return y
 
 
@@ -159,8 +181,9 @@ def lightgcn_propagate_raw(a: DeviceCSR, e0: torch.Tensor, n_layers: int, sum_re
         return e0.clone()
     layers = torch.empty((max(n_layers - 1, 1), n, d), dtype=torch.float32, device=e0.device) if n_layers > 1 else None
     ws, ws_bytes = _ws(a, d)
-    _lib.check(_lib.lib().hgr_lightgcn_forward_f32(C.byref(a.desc), e0.data_ptr(), _lib.ptr(layers), out.data_ptr(), n_layers, d,
-                                                   int(sum_readout), ws, ws_bytes, _lib.stream_ptr()))
+    with _Timed(n_layers):
+        _lib.check(_lib.lib().hgr_lightgcn_forward_f32(C.byref(a.desc), e0.data_ptr(), _lib.ptr(layers), out.data_ptr(), n_layers, d,
+                                                       int(sum_readout), ws, ws_bytes, _lib.stream_ptr()))
     return out
 
 

@@ -94,7 +94,7 @@ typedef struct {
  * `epi` may be NULL.  Deterministic: the same inputs give the same bits on every run. */
 size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D);
 /* Tuning hook: gather-batch depth x resident blocks per SM of the propagation kernel
- * (0: 8 x 3, 1: 8 x 4, 2: 16 x 2, 3: 4 x 6, 4: 8 x 5).  Results do not depend on it. */
+ * (0: 4 x 6 [default], 1: 8 x 3, 2: 8 x 4, 3: 4 x 5, 4: 2 x 8).  Results do not depend on it. */
 int hgr_set_spmm_variant(int variant);
 int hgr_spmm_f32(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi,
                  void *workspace, size_t workspace_bytes, hgr_stream_t stream);

@@ -183,3 +183,45 @@ def test_fullrank_eval_and_metrics(golden, pl_graph):
     ids_x, _ = O.fullrank_topk(golden["eval_user_emb"], golden["eval_item_emb"], test_users, tip, tix, 20, mode="exact")
     for a, b in zip(ids, ids_x):
         assert len(set(b)) == 20 and set(a) <= set(b)
+
+
+# ------------------------------------------------------------------------------------ torch restatement (CPU baseline arm)
+def test_torch_path_encoders_match_reference(golden, pl_graph):
+    import torch
+
+    from oracle import torch_path as T
+
+    torch.set_num_threads(1)
+    n = pl_graph["n_users"] + pl_graph["n_items"]
+    adj = T.coo_from_csr(*pl_graph["csr"], (n, n))
+    lae = T.LocalAwareEncoder(adj, pl_graph["n_users"], 64, 2)
+    lae.load_state_dict({k: torch.from_numpy(v) for k, v in params(golden, "lae_param/").items()}, strict=True)
+    lae.eval()
+    e0 = torch.from_numpy(golden["lae_E0"]).requires_grad_(True)
+    lu, li = lae(e0)
+    assert rel_err(lu.detach().numpy(), golden["lae_user_out"]) < RTOL and rel_err(li.detach().numpy(), golden["lae_item_out"]) < RTOL
+    (torch.cat([lu, li], 0) * torch.from_numpy(golden["spmm_G"])).sum().backward()
+    assert rel_err(e0.grad.numpy(), golden["lae_dE0"]) < RTOL
+    lg = T.LGCN(adj, pl_graph["n_users"], pl_graph["n_items"], 64, 3)
+    lg.load_state_dict({"embedding_dict.user_emb": torch.from_numpy(golden["lgcn_user_emb0"]),
+                        "embedding_dict.item_emb": torch.from_numpy(golden["lgcn_item_emb0"])})
+    with torch.no_grad():
+        ue, ie = lg()
+    assert np.array_equal(ue.numpy(), golden["lgcn_user_out"]) and np.array_equal(ie.numpy(), golden["lgcn_item_out"])
+
+
+def test_torch_path_losses_and_eval_match_reference(golden, pl_graph):
+    import torch
+
+    from oracle import torch_path as T
+
+    ut = torch.from_numpy(golden["loss_user_tab"])
+    it = torch.from_numpy(golden["loss_item_tab"])
+    u, p, n = (torch.from_numpy(golden[k]) for k in ("tri_u", "tri_p", "tri_n"))
+    assert rel_err(T.bpr_loss(ut[u], it[p], it[n]).numpy(), golden["loss_bpr"]) < 1e-6
+    assert rel_err((T.l2_reg_loss(0.1, ut[u], it[p], it[n]) / 2048).numpy(), golden["loss_reg"]) < 1e-6
+    user = {r: k for k, r in enumerate(golden["pl_id2user"])}
+    test_users = np.array([user[int(r)] for r in golden["eval_users_raw"]])
+    tip, tix, _ = O.interaction_matrix(pl_graph["u"], pl_graph["i"], pl_graph["n_users"], pl_graph["n_items"])
+    rec = T.evaluate_users(torch.from_numpy(golden["eval_user_emb"]), torch.from_numpy(golden["eval_item_emb"]), test_users, tip, tix, 20)
+    assert np.array_equal(golden["pl_id2item"][rec], golden["eval_rec_items_raw"])
