@@ -1,0 +1,842 @@
+// Full-ranking evaluation: user x item score contraction fused with training-item masking and a
+// per-user top-K, sm_100a.
+//
+// Replaces GraphRecommender.test (base/graph_recommender.py:61-92 = base/main_recommender.py:64-100):
+//   for user in test_set:  candidates = predict(user)            # torch.matmul(user_emb[u], item_emb.T).cpu()
+//                          candidates[train items of user] = -10e8
+//                          ids, scores = find_k_largest(max_N, candidates)      # util/algorithm.py:143-173
+// i.e. one GEMV + a PCIe copy of n_items floats + a python mask loop + a numba insertion top-K per user.
+//
+// Pipeline (all on the caller's stream, no host synchronisation):
+//   1. eval_pack_kernel      fp32 tables -> bf16 in the tcgen05 K-major no-swizzle core-matrix layout
+//                            (8 rows x 16 B core matrices; an 8-row group is 1 KB), row norms for the
+//                            error bound.  A tile is then ONE contiguous block: a single cp.async.bulk.
+//   2. eval_candidates_kernel  the dense step.  CTA = 256 test users x a range of item tiles (128 items).
+//                            warp 0: bulk-copy producer (4-stage mbarrier ring); warp 1: one thread issues
+//                            tcgen05.mma kind::f16 (bf16 x bf16 -> fp32, M128 N128 K16 x 4 per half) into
+//                            a double-buffered TMEM accumulator (2 stages x 2 halves x 128 columns = 512);
+//                            warps 2..9: epilogue, tcgen05.ld 32x32b (thread = user row), training items
+//                            poisoned to NaN from the train CSR row, running K-th-best threshold per user
+//                            kept in a sorted shared-memory list updated warp-cooperatively, elements above
+//                            (threshold - 2 eps) appended to the user's candidate list.  Scores never leave
+//                            the SM; only ~K ln(I/K) (score, id) pairs per user do.
+//   3. eval_rescore_kernel   exact fp32 re-scoring of the surviving candidates in the canonical order
+//                            (ascending-k fused multiply-add, oracle/hgr_oracle.c hgr_oracle_scores_f32) and
+//                            exact top-K: score descending, ties by ascending item id.  Because
+//                            |bf16 score - fp32 score| <= eps(user) is a proven bound, the candidate set is a
+//                            superset of the true top-K and the result is bit-identical to the oracle.
+//   4. eval_brute_kernel     exact SIMT fallback for users whose candidate list overflowed (and the whole
+//                            job when D != 64 or K > 64): every score in fp32, K rounds of block arg-max.
+//   5. eval_refquirk_kernel  optional: replays find_k_largest's re-visit of the first K candidates
+//                             so that Recall/NDCG strings match the reference bit for bit.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+#include <string.h>
+#include <limits.h>
+
+#include "hgr_internal.cuh"
+
+namespace hgr {
+
+// ------------------------------------------------------------------------------------------ constants
+constexpr int EV_D = 64;           // embedding width of the tensor path (one 128-byte bf16 row)
+constexpr int EV_BM = 256;         // users per CTA: two 128-row accumulators
+constexpr int EV_BN = 128;         // items per tile
+constexpr int EV_STAGES = 4;       // item tiles in flight
+constexpr int EV_A_BYTES = EV_BM * EV_D * 2;        // 32 KB
+constexpr int EV_B_BYTES = EV_BN * EV_D * 2;        // 16 KB
+constexpr int EV_EPI_WARPS = 8;
+constexpr int EV_THREADS = 64 + 32 * EV_EPI_WARPS;  // producer warp, MMA warp, 8 epilogue warps
+constexpr int EV_TMEM_COLS = 512;
+constexpr float EV_MASK_SCORE = -10e8f;             // base/graph_recommender.py:80
+// |sum_k bf16(u_k) bf16(i_k) - fl32(sum_k u_k i_k)| <= EV_EPS_REL * ||u||_2 * ||i||_2 :
+// two bf16 roundings (2^-8 each, round to nearest) give (1 + 2^-8)^2 - 1 < 2^-7 (1 + 2^-9) per product,
+// Cauchy-Schwarz turns sum |u_k i_k| into the norm product, and the two fp32 accumulations add at most
+// 2 * 64 * 2^-23 of it.  0.0082 = 2^-7 * 1.05 covers all of it and the rounding of the norms themselves.
+constexpr float EV_EPS_REL = 0.0082f;
+
+struct EvalParams {
+    const __nv_bfloat16 *Ap;  // packed test-user rows [n_test_pad / 8][8 chunks][8 rows][8]
+    const __nv_bfloat16 *Bp;  // packed item rows      [n_items_pad / 8][...]
+    const float *slack;       // [n_test_pad] 2 * eps(user)
+    const int32_t *test_users;
+    const int64_t *train_indptr;
+    const int32_t *train_indices;
+    float2 *cand;        // [n_splits][n_test_pad][cap] (approx score, item id bits)
+    int32_t *cand_cnt;   // [n_splits][n_test_pad]
+    float *cand_tau;     // [n_splits][n_test_pad] K-th best approx score seen by the split
+    int32_t *overflow;   // [n_test_pad]
+    int32_t n_test, n_items, n_tiles, tiles_per_split, cap, K;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+// Bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between the two core matrices an
+// MMA reads along K (128 B), SBO = distance between 8-row groups (1024 B); descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// c = f32 (1 << 4), a = b = bf16 (1 << 7, 1 << 10), both K-major, N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr uint32_t EV_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(EV_BN >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------ 1. pack
+// One thread = one (row, 8-element chunk): fp32 -> bf16, written as one 16-byte store into the core-matrix
+// layout.  The 8 threads of a row reduce the squared norm; users store 2 * eps, items a global max norm.
+__global__ void __launch_bounds__(256) eval_pack_kernel(const float *__restrict__ tab, const int32_t *__restrict__ gather,
+                                                        int64_t n_rows, int64_t n_rows_pad, int64_t n_tab_rows,
+                                                        __nv_bfloat16 *__restrict__ out, float *__restrict__ row_norm,
+                                                        unsigned int *__restrict__ max_norm_bits) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t row = t >> 3;
+    const int chunk = (int)(t & 7);
+    if (row >= n_rows_pad) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    bool live = row < n_rows;
+    if (live) {
+        int64_t src = gather ? (int64_t)gather[row] : row;
+        if (src < 0 || src >= n_tab_rows) live = false;
+        else {
+            const float4 *p = reinterpret_cast<const float4 *>(tab + src * EV_D + chunk * 8);
+            a = __ldg(p);
+            b = __ldg(p + 1);
+        }
+    }
+    __nv_bfloat162 q[4];
+    q[0] = __floats2bfloat162_rn(a.x, a.y);
+    q[1] = __floats2bfloat162_rn(a.z, a.w);
+    q[2] = __floats2bfloat162_rn(b.x, b.y);
+    q[3] = __floats2bfloat162_rn(b.z, b.w);
+    const int64_t off = (row >> 3) * 512 + chunk * 64 + (row & 7) * 8;  // in bf16 elements
+    *reinterpret_cast<uint4 *>(out + off) = *reinterpret_cast<const uint4 *>(q);
+    float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w) + (b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    if (chunk == 0) {
+        const float nrm = sqrtf(ss) * 1.0001f;
+        if (row_norm) row_norm[row] = live ? nrm : 0.f;
+        if (max_norm_bits && live) atomicMax(max_norm_bits, __float_as_uint(nrm));  // nrm >= 0: bit order = value order
+    }
+}
+
+// slack[row] = 2 * eps = 2 * EV_EPS_REL * ||u|| * max ||i||
+__global__ void eval_slack_kernel(float *__restrict__ slack, int64_t n, const unsigned int *__restrict__ max_norm_bits) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) slack[r] = 2.0f * EV_EPS_REL * slack[r] * __uint_as_float(*max_norm_bits) + 1e-30f;
+}
+
+// ------------------------------------------------------------------------------------------ 2. candidates
+struct EvalSmem {
+    // offsets into dynamic shared memory (base aligned to 1024)
+    static constexpr int A = 0;
+    static constexpr int B = A + EV_A_BYTES;
+    static constexpr int LISTS = B + EV_STAGES * EV_B_BYTES;
+};
+
+// Warp-cooperative handling of one 4-column group in which at least one lane (= user row) saw a value at or
+// above its threshold.  All 32 lanes work on one such row at a time: the row's sorted list of its K best
+// approximate scores lives in shared memory, one slot per lane (two when KPAD == 64).
+struct EvRowState {
+    float thr;  // running K-th best approximate score minus 2 eps; +inf for padding rows
+    int cnt;    // candidates appended so far
+};
+
+template <int KPAD>
+__device__ __noinline__ EvRowState eval_group_events(unsigned hits, float x0, float x1, float x2, float x3, int col, float thr,
+                                                     int cnt, float slack, float *__restrict__ lists,
+                                                     float2 *__restrict__ cand_rows, int32_t *__restrict__ overflow_rows,
+                                                     int n_items, int cap, int K) {
+    const int lane = threadIdx.x & 31;
+    while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        float y[4];
+        y[0] = __shfl_sync(0xffffffffu, x0, src);
+        y[1] = __shfl_sync(0xffffffffu, x1, src);
+        y[2] = __shfl_sync(0xffffffffu, x2, src);
+        y[3] = __shfl_sync(0xffffffffu, x3, src);
+        float thr_s = __shfl_sync(0xffffffffu, thr, src);
+        const float slack_s = __shfl_sync(0xffffffffu, slack, src);
+        int cnt_s = __shfl_sync(0xffffffffu, cnt, src);
+        float *list = lists + src * KPAD;
+        float2 *crow = cand_rows + (int64_t)src * cap;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v = y[e];
+            const int c = col + e;
+            if (v >= thr_s && c < n_items) {  // warp-uniform
+                if (cnt_s < cap) {
+                    if (lane == 0) crow[cnt_s] = make_float2(v, __int_as_float(c));
+                } else if (lane == 0) {
+                    overflow_rows[src] = 1;
+                }
+                ++cnt_s;
+                if (KPAD == 32) {
+                    const float cur = list[lane];
+                    const int pos = __popc(__ballot_sync(0xffffffffu, cur >= v));
+                    if (pos < K) {
+                        const float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                        const float nv = lane < pos ? cur : (lane == pos ? v : up);
+                        list[lane] = nv;
+                        thr_s = __shfl_sync(0xffffffffu, nv, K - 1) - slack_s;
+                    }
+                } else {
+                    const float c0 = list[lane], c1 = list[32 + lane];
+                    const int pos = __popc(__ballot_sync(0xffffffffu, c0 >= v)) + __popc(__ballot_sync(0xffffffffu, c1 >= v));
+                    if (pos < K) {
+                        const float u0 = __shfl_up_sync(0xffffffffu, c0, 1);
+                        float u1 = __shfl_up_sync(0xffffffffu, c1, 1);
+                        const float c31 = __shfl_sync(0xffffffffu, c0, 31);
+                        if (lane == 0) u1 = c31;
+                        const float n0 = lane < pos ? c0 : (lane == pos ? v : u0);
+                        const float n1 = (32 + lane) < pos ? c1 : ((32 + lane) == pos ? v : u1);
+                        list[lane] = n0;
+                        list[32 + lane] = n1;
+                        const float tau = (K <= 32) ? __shfl_sync(0xffffffffu, n0, (K - 1) & 31)
+                                                    : __shfl_sync(0xffffffffu, n1, (K - 33) & 31);
+                        thr_s = tau - slack_s;
+                    }
+                }
+            }
+        }
+        if (lane == src) {
+            thr = thr_s;
+            cnt = cnt_s;
+        }
+    }
+    EvRowState out;
+    out.thr = thr;
+    out.cnt = cnt;
+    return out;
+}
+
+template <int KPAD>
+__global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const EvalParams P) {
+    extern __shared__ uint8_t ev_smem_raw[];
+    // 1024-byte aligned view of dynamic shared memory
+    const uint32_t raw = smem_u32(ev_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *sm = ev_smem_raw + (base - raw);
+    float *lists_all = reinterpret_cast<float *>(sm + EvalSmem::LISTS);  // [8 warps][32 rows][KPAD]
+    __shared__ __align__(8) uint64_t bars[2 * EV_STAGES + 1 + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x, split = blockIdx.y;
+    const int tile0 = split * P.tiles_per_split;
+    const int tile1 = min(tile0 + P.tiles_per_split, P.n_tiles);
+    const int n_my = tile1 - tile0;
+
+    const uint32_t bar_full = smem_u32(&bars[0]);               // [EV_STAGES]
+    const uint32_t bar_empty = smem_u32(&bars[EV_STAGES]);      // [EV_STAGES]
+    const uint32_t bar_a = smem_u32(&bars[2 * EV_STAGES]);
+    const uint32_t bar_tfull = smem_u32(&bars[2 * EV_STAGES + 1]);   // [2]
+    const uint32_t bar_tempty = smem_u32(&bars[2 * EV_STAGES + 3]);  // [2]
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < EV_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, EV_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)EV_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {  // every row's best-K list starts at -inf
+        float *l = lists_all + (warp - 2) * 32 * KPAD;
+        for (int j = lane; j < 32 * KPAD; j += 32) l[j] = -CUDART_INF_F;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== producer: one 32 KB bulk copy for the user block, one 16 KB bulk copy per item tile =====
+        if (lane == 0 && n_my > 0) {
+            mbar_arrive_expect_tx(bar_a, EV_A_BYTES);
+            bulk_copy_g2s(base + EvalSmem::A, reinterpret_cast<const uint8_t *>(P.Ap) + (int64_t)m_blk * EV_A_BYTES, EV_A_BYTES,
+                          bar_a);
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it % EV_STAGES;
+                const uint32_t ph = (it / EV_STAGES) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                mbar_arrive_expect_tx(bar_full + 8 * s, EV_B_BYTES);
+                bulk_copy_g2s(base + EvalSmem::B + s * EV_B_BYTES,
+                              reinterpret_cast<const uint8_t *>(P.Bp) + (int64_t)(tile0 + it) * EV_B_BYTES, EV_B_BYTES,
+                              bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0 && n_my > 0) {
+            mbar_wait(bar_a, 0);
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it % EV_STAGES;
+                const uint32_t ph = (it / EV_STAGES) & 1;
+                const int as = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aph ^ 1);  // epilogue drained this accumulator stage
+                mbar_wait(bar_full + 8 * s, ph);          // item tile landed
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t d = tmem_base + (uint32_t)(as * 256 + h * 128);
+#pragma unroll
+                    for (int k = 0; k < EV_D / 16; ++k) {
+                        const uint64_t da = umma_desc(base + EvalSmem::A + h * (EV_A_BYTES / 2) + k * 256);
+                        const uint64_t db = umma_desc(base + EvalSmem::B + s * EV_B_BYTES + k * 256);
+                        tc_mma_bf16(d, da, db, EV_IDESC, k > 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar_empty + 8 * s);    // smem slot reusable once these MMAs have read it
+                tc_commit(bar_tfull + 8 * as);   // accumulators ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps, thread = one user row of one 128-row half =====
+        const int ew = warp - 2;
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int half = ew >> 2;
+        const int row_in_cta = half * 128 + quad * 32 + lane;
+        const int64_t row = (int64_t)m_blk * EV_BM + row_in_cta;
+        const bool live = row < P.n_test;
+        const int64_t n_pad = (int64_t)gridDim.x * EV_BM;
+        float *lists = lists_all + ew * 32 * KPAD;
+        // rows of this warp are consecutive: row - lane is lane 0's row
+        float2 *cand_rows = P.cand + ((int64_t)split * n_pad + (row - lane)) * P.cap;
+        int32_t *overflow_rows = P.overflow + (row - lane);
+        float thr = live ? -CUDART_INF_F : CUDART_INF_F;
+        const float slack = live ? P.slack[row] : 0.f;
+        int cnt = 0;
+        // training items of this user at or after the split's first column, walked in step with the columns
+        int64_t tp = 0, tend = 0;
+        if (live) {
+            const int32_t u = P.test_users[row];
+            tp = P.train_indptr[u];
+            tend = P.train_indptr[u + 1];
+            const int first_col = tile0 * EV_BN;
+            int64_t lo = tp, hi = tend;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (P.train_indices[mid] < first_col) lo = mid + 1;
+                else hi = mid;
+            }
+            tp = lo;
+        }
+        int nt0 = tp < tend ? __ldg(P.train_indices + tp) : INT_MAX;
+        int nt1 = tp + 1 < tend ? __ldg(P.train_indices + tp + 1) : INT_MAX;
+
+        for (int it = 0; it < n_my; ++it) {
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + half * 128);
+            const int col_tile = (tile0 + it) * EV_BN;
+#pragma unroll 1
+            for (int c = 0; c < EV_BN / 32; ++c) {
+                uint32_t raw32[32];
+                tc_ld32(tcol + c * 32, raw32);
+                tc_ld_wait();
+                const int col0 = col_tile + c * 32;
+                if (nt0 < col0 + 32) {  // this user has training items among these 32 columns: poison them
+                    unsigned mb = 0;
+                    do {
+                        mb |= 1u << (nt0 - col0);
+                        nt0 = nt1;
+                        ++tp;
+                        nt1 = tp + 1 < tend ? __ldg(P.train_indices + tp + 1) : INT_MAX;
+                    } while (nt0 < col0 + 32);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (mb & (1u << j)) raw32[j] = 0x7fc00000u;  // NaN: never >= a threshold, ignored by fmaxf
+                }
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float x0 = __uint_as_float(raw32[4 * g]), x1 = __uint_as_float(raw32[4 * g + 1]);
+                    const float x2 = __uint_as_float(raw32[4 * g + 2]), x3 = __uint_as_float(raw32[4 * g + 3]);
+                    const float m = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+                    const unsigned hits = __ballot_sync(0xffffffffu, m >= thr);
+                    if (hits) {
+                        const EvRowState rs = eval_group_events<KPAD>(hits, x0, x1, x2, x3, col0 + 4 * g, thr, cnt, slack, lists,
+                                                                      cand_rows, overflow_rows, P.n_items, P.cap, P.K);
+                        thr = rs.thr;
+                        cnt = rs.cnt;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        }
+        __syncwarp();
+        if (live) {
+            P.cand_cnt[(int64_t)split * n_pad + row] = min(cnt, P.cap);
+            P.cand_tau[(int64_t)split * n_pad + row] = lists[lane * KPAD + (P.K - 1)];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)EV_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exact helpers
+__device__ __forceinline__ uint32_t orderable(float s) {
+    if (s == 0.f) s = 0.f;  // -0 and +0 tie
+    const uint32_t b = __float_as_uint(s);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+// larger key = better: score descending, then item id ascending
+__device__ __forceinline__ unsigned long long rank_key(float s, int id) {
+    return ((unsigned long long)orderable(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)id);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+        k = other > k ? other : k;
+    }
+    return k;
+}
+// canonical score: ascending-k fused multiply-add chain (oracle/hgr_oracle.c hgr_oracle_scores_f32)
+__device__ __forceinline__ float exact_score(const float *__restrict__ u_sm, const float *__restrict__ item_row, int D) {
+    float acc = 0.f;
+    const float4 *p = reinterpret_cast<const float4 *>(item_row);
+    for (int k = 0; k < D / 4; ++k) {
+        const float4 q = __ldg(p + k);
+        acc = fmaf(u_sm[4 * k], q.x, acc);
+        acc = fmaf(u_sm[4 * k + 1], q.y, acc);
+        acc = fmaf(u_sm[4 * k + 2], q.z, acc);
+        acc = fmaf(u_sm[4 * k + 3], q.w, acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ bool is_train_item(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int v) {
+    const int64_t end = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo < end && __ldg(a + lo) == v;
+}
+
+// ------------------------------------------------------------------------------------------ 3. rescore
+constexpr int RS_WARPS = 4;
+constexpr int RS_CAP = 512;  // surviving candidates per user kept in shared memory
+
+__global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
+    const float *__restrict__ user_emb, const float *__restrict__ item_emb, int D, const int32_t *__restrict__ test_users,
+    const int64_t *__restrict__ train_indptr, const int32_t *__restrict__ train_indices, const float2 *__restrict__ cand,
+    const int32_t *__restrict__ cand_cnt, const float *__restrict__ cand_tau, const float *__restrict__ slack,
+    int32_t *__restrict__ overflow, int n_splits, int64_t n_pad, int cap, int n_test, int K, int32_t *__restrict__ out_ids,
+    float *__restrict__ out_scores, unsigned long long *__restrict__ stats) {
+    __shared__ float u_sm[RS_WARPS][128];
+    __shared__ unsigned long long keys[RS_WARPS][RS_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= n_test) return;
+    if (overflow[row]) return;  // handled by eval_brute_kernel
+    const int32_t u = test_users[row];
+    for (int k = lane; k < D; k += 32) u_sm[warp][k] = user_emb[(int64_t)u * D + k];
+    // a split's K-th best approximate score bounds the global K-th best from below
+    float tau = -CUDART_INF_F;
+    for (int s = 0; s < n_splits; ++s) tau = fmaxf(tau, cand_tau[(int64_t)s * n_pad + row]);
+    const float keep = tau - slack[row];
+    __syncwarp();
+    int n_keep = 0;
+    unsigned long long seen = 0;
+    for (int s = 0; s < n_splits; ++s) {
+        const int cnt = cand_cnt[(int64_t)s * n_pad + row];
+        const float2 *crow = cand + ((int64_t)s * n_pad + row) * cap;
+        seen += (unsigned long long)cnt;
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = false;
+            int id = 0;
+            float sc = 0.f;
+            if (j < cnt) {
+                const float2 c = crow[j];
+                id = __float_as_int(c.y);
+                ok = c.x >= keep;
+                if (ok) sc = exact_score(u_sm[warp], item_emb + (int64_t)id * D, D);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int slot = n_keep + __popc(m & ((1u << lane) - 1u));
+            if (ok && slot < RS_CAP) keys[warp][slot] = rank_key(sc, id);
+            n_keep += __popc(m);
+        }
+    }
+    if (n_keep > RS_CAP) {  // cannot happen with sane thresholds; route the row to the exact fallback
+        if (lane == 0) overflow[row] = 1;
+        return;
+    }
+    __syncwarp();
+    if (lane == 0 && stats) {
+        atomicAdd(stats + 0, seen);
+        atomicAdd(stats + 1, (unsigned long long)n_keep);
+    }
+    // K rounds: best key strictly below the previous winner
+    unsigned long long prev = ~0ull;
+    int filled = 0;
+    for (int r = 0; r < K; ++r) {
+        unsigned long long best = 0ull;
+        for (int j = lane; j < n_keep; j += 32) {
+            const unsigned long long k = keys[warp][j];
+            if (k < prev && k > best) best = k;
+        }
+        best = warp_max_u64(best);
+        if (best == 0ull) break;
+        prev = best;
+        if (lane == 0) {
+            const uint32_t ob = (uint32_t)(best >> 32);
+            const uint32_t fb = (ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob;
+            out_ids[row * K + r] = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffu));
+            out_scores[row * K + r] = __uint_as_float(fb);
+        }
+        ++filled;
+    }
+    // fewer than K unmasked items in the whole catalogue: the reference then returns masked items
+    // (-10e8) in ascending id order (oracle topk_exact keeps them as candidates)
+    const int64_t t0 = train_indptr[u], t1 = train_indptr[u + 1];
+    for (int r = filled + lane; r < K; r += 32) {
+        const int64_t q = t0 + (r - filled);
+        out_ids[row * K + r] = q < t1 ? train_indices[q] : -1;
+        out_scores[row * K + r] = EV_MASK_SCORE;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 4. brute force
+constexpr int BF_THREADS = 256;
+
+// Block per user: every item scored in fp32 in the canonical order into a scratch row, training items
+// overwritten with -10e8, then K rounds of block-wide arg-max under the previous winner.
+// only_overflow != 0: process only rows flagged by the tensor path.
+__global__ void __launch_bounds__(BF_THREADS) eval_brute_kernel(const float *__restrict__ user_emb,
+                                                                const float *__restrict__ item_emb, int D, int n_items,
+                                                                const int32_t *__restrict__ test_users,
+                                                                const int64_t *__restrict__ train_indptr,
+                                                                const int32_t *__restrict__ train_indices,
+                                                                const int32_t *__restrict__ overflow, int only_overflow,
+                                                                int n_test, int K, float *__restrict__ scratch,
+                                                                int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                                unsigned long long *__restrict__ stats) {
+    __shared__ float u_sm[128];
+    __shared__ unsigned long long red[BF_THREADS / 32];
+    __shared__ unsigned long long winner;
+    float *srow = scratch + (int64_t)blockIdx.x * n_items;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int row = blockIdx.x; row < n_test; row += gridDim.x) {
+        if (only_overflow && !overflow[row]) continue;
+        const int32_t u = test_users[row];
+        __syncthreads();
+        for (int k = threadIdx.x; k < D; k += BF_THREADS) u_sm[k] = user_emb[(int64_t)u * D + k];
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_items; i += BF_THREADS) srow[i] = exact_score(u_sm, item_emb + (int64_t)i * D, D);
+        __syncthreads();
+        for (int64_t q = train_indptr[u] + threadIdx.x; q < train_indptr[u + 1]; q += BF_THREADS) {
+            const int it = train_indices[q];
+            if (it >= 0 && it < n_items) srow[it] = EV_MASK_SCORE;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && stats && only_overflow) atomicAdd(stats + 2, 1ull);
+        unsigned long long prev = ~0ull;
+        for (int r = 0; r < K; ++r) {
+            unsigned long long best = 0ull;
+            for (int i = threadIdx.x; i < n_items; i += BF_THREADS) {
+                const unsigned long long k = rank_key(srow[i], i);
+                if (k < prev && k > best) best = k;
+            }
+            best = warp_max_u64(best);
+            if (lane == 0) red[warp] = best;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long b = 0ull;
+                for (int w = 0; w < BF_THREADS / 32; ++w) b = red[w] > b ? red[w] : b;
+                winner = b;
+                if (b != 0ull) {
+                    const int id = (int32_t)(0xffffffffu - (uint32_t)(b & 0xffffffffu));
+                    out_ids[(int64_t)row * K + r] = id;
+                    out_scores[(int64_t)row * K + r] = srow[id];
+                } else {
+                    out_ids[(int64_t)row * K + r] = -1;
+                    out_scores[(int64_t)row * K + r] = EV_MASK_SCORE;
+                }
+            }
+            __syncthreads();
+            prev = winner;
+            if (prev == 0ull) prev = 1ull;  // nothing left: later rounds find nothing either
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 5. refquirk
+// find_k_largest (util/algorithm.py:143-173) seeds its list with candidates[0:K] sorted by score and then
+// visits EVERY candidate again, including those first K.  Its result is the first K entries
+// of the stable merge of  A = items 0..K-1 sorted (score desc, id asc)  and  B = the exact top-K,
+// with A's entries first on equal scores.  One warp per user; K <= 64.
+__global__ void __launch_bounds__(128) eval_refquirk_kernel(const float *__restrict__ user_emb,
+                                                            const float *__restrict__ item_emb, int D,
+                                                            const int32_t *__restrict__ test_users,
+                                                            const int64_t *__restrict__ train_indptr,
+                                                            const int32_t *__restrict__ train_indices, int n_test, int K,
+                                                            int32_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+    __shared__ float u_sm[4][128];
+    __shared__ float a_s[4][64], b_s[4][64];
+    __shared__ int b_id[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+    if (row >= n_test) return;
+    const int32_t u = test_users[row];
+    for (int k = lane; k < D; k += 32) u_sm[warp][k] = user_emb[(int64_t)u * D + k];
+    __syncwarp();
+    const int64_t t0 = train_indptr[u], t1 = train_indptr[u + 1];
+    for (int j = lane; j < K; j += 32) {
+        float s = exact_score(u_sm[warp], item_emb + (int64_t)j * D, D);
+        if (is_train_item(train_indices, t0, t1, j)) s = EV_MASK_SCORE;
+        a_s[warp][j] = s;
+        b_s[warp][j] = out_scores[row * K + j];
+        b_id[warp][j] = out_ids[row * K + j];
+    }
+    __syncwarp();
+    for (int j = lane; j < K; j += 32) {
+        // position of A_j in the merge: A entries ahead of it + B entries with a strictly larger score
+        const float s = a_s[warp][j];
+        int pos = 0;
+        for (int l = 0; l < K; ++l) {
+            const float t = a_s[warp][l];
+            pos += (t > s) || (t == s && l < j);
+            pos += b_s[warp][l] > s;
+        }
+        if (pos < K) {
+            out_ids[row * K + pos] = j;
+            out_scores[row * K + pos] = s;
+        }
+        // position of B_j: B entries ahead of it (B is already sorted) + A entries with score >= its score
+        const float sb = b_s[warp][j];
+        int pb = j;
+        for (int l = 0; l < K; ++l) pb += a_s[warp][l] >= sb;
+        if (pb < K) {
+            out_ids[row * K + pb] = b_id[warp][j];
+            out_scores[row * K + pb] = sb;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct EvalPlan {
+    int64_t n_test_pad, n_items_pad;
+    int n_tiles, n_splits, tiles_per_split, cap, kpad, n_brute_blocks;
+    size_t off_ap, off_bp, off_slack, off_maxnorm, off_cand, off_cnt, off_tau, off_overflow, off_scratch, total;
+    bool tensor;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int engine) {
+    EvalPlan p;
+    memset(&p, 0, sizeof(p));
+    p.tensor = engine != 1 && D == EV_D && K <= 64 && n_test > 0;
+    p.n_test_pad = ceil_div(n_test > 0 ? n_test : 1, EV_BM) * EV_BM;
+    p.n_items_pad = ceil_div(n_items > 0 ? n_items : 1, EV_BN) * EV_BN;
+    p.n_tiles = (int)(p.n_items_pad / EV_BN);
+    p.kpad = K <= 32 ? 32 : 64;
+    p.cap = K <= 32 ? 512 : 1024;
+    // enough CTAs to fill 148 SMs about twice, but never fewer than 8 tiles per split
+    const int64_t m_blocks = p.n_test_pad / EV_BM;
+    int splits = (int)ceil_div(2 * 148, m_blocks);
+    const int max_splits = p.n_tiles / 8 > 0 ? p.n_tiles / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = (int)ceil_div(p.n_tiles, splits);
+    p.n_splits = (int)ceil_div(p.n_tiles, p.tiles_per_split);
+    p.n_brute_blocks = p.tensor ? 148 : 148 * 4;
+    if (p.n_brute_blocks > n_test && n_test > 0) p.n_brute_blocks = (int)n_test;
+    size_t o = 0;
+    if (p.tensor) {
+        p.off_ap = o; o = align_up(o + (size_t)p.n_test_pad * EV_D * 2, 256);
+        p.off_bp = o; o = align_up(o + (size_t)p.n_items_pad * EV_D * 2, 256);
+        p.off_slack = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
+        p.off_maxnorm = o; o = align_up(o + 256, 256);
+        p.off_cand = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * p.cap * 8, 256);
+        p.off_cnt = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * 4, 256);
+        p.off_tau = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * 4, 256);
+    }
+    p.off_overflow = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
+    p.off_scratch = o; o = align_up(o + (size_t)p.n_brute_blocks * (size_t)(n_items > 0 ? n_items : 1) * 4, 256);
+    p.total = o;
+    return p;
+}
+
+}  // namespace hgr
+
+extern "C" {
+
+size_t hgr_fullrank_topk_workspace_bytes(int64_t n_test, int64_t n_items, int32_t D, int32_t K, int32_t engine) {
+    if (n_test < 0 || n_items <= 0 || K <= 0) return 0;
+    return hgr::make_plan(n_test, n_items, D, K, engine).total;
+}
+
+int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *item_emb, int64_t n_items, int32_t D,
+                          const int32_t *test_users, int64_t n_test, const int64_t *train_indptr,
+                          const int32_t *train_indices, int32_t K, int32_t mode, int32_t engine, int32_t *out_ids,
+                          float *out_scores, uint64_t *stats, void *workspace, size_t workspace_bytes,
+                          hgr_stream_t stream) {
+    using namespace hgr;
+    cudaStream_t st = (cudaStream_t)stream;
+    HGR_REQUIRE(n_test >= 0 && n_users > 0 && n_items > 0, "negative or empty dimension");
+    HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
+    HGR_REQUIRE(K >= 1 && K <= n_items, "K = %d must be in [1, n_items = %lld]", K, (long long)n_items);
+    HGR_REQUIRE(mode == 0 || mode == 1, "mode %d unknown (0 exact, 1 refquirk)", mode);
+    HGR_REQUIRE(engine >= 0 && engine <= 2, "engine %d unknown (0 auto, 1 simt, 2 tensor)", engine);
+    HGR_REQUIRE(mode == 0 || K <= 64, "refquirk mode supports K <= 64, got %d", K);
+    HGR_REQUIRE(n_items < (int64_t)0x7fffff00 && n_test < (int64_t)0x7fffff00, "dimension does not fit int32");
+    if (n_test == 0) return HGR_OK;
+    HGR_REQUIRE(user_emb && item_emb && test_users && train_indptr && out_ids && out_scores, "NULL argument");
+    HGR_REQUIRE(aligned16(user_emb) && aligned16(item_emb), "embedding tables must be 16-byte aligned");
+    const EvalPlan p = make_plan(n_test, n_items, D, K, engine);
+    HGR_REQUIRE(engine != 2 || p.tensor, "tensor engine needs D == 64 and K <= 64");
+    if (workspace == nullptr || workspace_bytes < p.total)
+        return set_error(HGR_ERR_WORKSPACE, "fullrank_topk workspace: need %zu bytes, got %zu", p.total, workspace_bytes);
+    HGR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    uint8_t *ws = static_cast<uint8_t *>(workspace);
+    int32_t *overflow = reinterpret_cast<int32_t *>(ws + p.off_overflow);
+    float *scratch = reinterpret_cast<float *>(ws + p.off_scratch);
+    unsigned long long *st64 = reinterpret_cast<unsigned long long *>(stats);
+    HGR_CUDA_OK(cudaMemsetAsync(overflow, 0, (size_t)p.n_test_pad * 4, st));
+
+    if (p.tensor) {
+        __nv_bfloat16 *Ap = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_ap);
+        __nv_bfloat16 *Bp = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_bp);
+        float *slack = reinterpret_cast<float *>(ws + p.off_slack);
+        unsigned int *maxnorm = reinterpret_cast<unsigned int *>(ws + p.off_maxnorm);
+        HGR_CUDA_OK(cudaMemsetAsync(maxnorm, 0, 4, st));
+        eval_pack_kernel<<<(unsigned)ceil_div(p.n_items_pad * 8, 256), 256, 0, st>>>(item_emb, nullptr, n_items, p.n_items_pad,
+                                                                                    n_items, Bp, nullptr, maxnorm);
+        HGR_LAUNCH_OK("eval_pack_kernel(items)");
+        eval_pack_kernel<<<(unsigned)ceil_div(p.n_test_pad * 8, 256), 256, 0, st>>>(user_emb, test_users, n_test, p.n_test_pad,
+                                                                                   n_users, Ap, slack, nullptr);
+        HGR_LAUNCH_OK("eval_pack_kernel(users)");
+        eval_slack_kernel<<<(unsigned)ceil_div(p.n_test_pad, 256), 256, 0, st>>>(slack, p.n_test_pad, maxnorm);
+        HGR_LAUNCH_OK("eval_slack_kernel");
+
+        EvalParams P;
+        P.Ap = Ap;
+        P.Bp = Bp;
+        P.slack = slack;
+        P.test_users = test_users;
+        P.train_indptr = train_indptr;
+        P.train_indices = train_indices;
+        P.cand = reinterpret_cast<float2 *>(ws + p.off_cand);
+        P.cand_cnt = reinterpret_cast<int32_t *>(ws + p.off_cnt);
+        P.cand_tau = reinterpret_cast<float *>(ws + p.off_tau);
+        P.overflow = overflow;
+        P.n_test = (int32_t)n_test;
+        P.n_items = (int32_t)n_items;
+        P.n_tiles = p.n_tiles;
+        P.tiles_per_split = p.tiles_per_split;
+        P.cap = p.cap;
+        P.K = K;
+        const size_t smem = 1024 + (size_t)EvalSmem::LISTS + (size_t)EV_EPI_WARPS * 32 * p.kpad * 4;
+        const dim3 grid((unsigned)(p.n_test_pad / EV_BM), (unsigned)p.n_splits);
+        if (p.kpad == 32) {
+            HGR_CUDA_OK(cudaFuncSetAttribute(eval_candidates_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            eval_candidates_kernel<32><<<grid, EV_THREADS, smem, st>>>(P);
+        } else {
+            HGR_CUDA_OK(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            eval_candidates_kernel<64><<<grid, EV_THREADS, smem, st>>>(P);
+        }
+        HGR_LAUNCH_OK("eval_candidates_kernel");
+        eval_rescore_kernel<<<(unsigned)ceil_div(n_test, RS_WARPS), RS_WARPS * 32, 0, st>>>(
+            user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, P.cand_tau, slack, overflow,
+            p.n_splits, p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
+        HGR_LAUNCH_OK("eval_rescore_kernel");
+    }
+    eval_brute_kernel<<<(unsigned)p.n_brute_blocks, BF_THREADS, 0, st>>>(user_emb, item_emb, D, (int)n_items, test_users,
+                                                                        train_indptr, train_indices, overflow, p.tensor ? 1 : 0,
+                                                                        (int)n_test, K, scratch, out_ids, out_scores, st64);
+    HGR_LAUNCH_OK("eval_brute_kernel");
+    if (mode == 1) {
+        eval_refquirk_kernel<<<(unsigned)ceil_div(n_test, 4), 128, 0, st>>>(user_emb, item_emb, D, test_users, train_indptr,
+                                                                           train_indices, (int)n_test, K, out_ids, out_scores);
+        HGR_LAUNCH_OK("eval_refquirk_kernel");
+    }
+    return HGR_OK;
+}
+
+}  // extern "C"

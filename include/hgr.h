@@ -182,6 +182,34 @@ int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
                        float batch_size_div, const void *saved, const float *grad_out, float *d_user_tab,
                        float *d_item_tab, hgr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Full-ranking evaluation: GraphRecommender.test (base/graph_recommender.py:61-92, identical in
+ * base/main_recommender.py:64-100) with predict (model/graph/LightGCN.py:99-102) and find_k_largest
+ * (util/algorithm.py:143-173) fused: for every test user the scores against ALL items, the user's
+ * training items replaced by -10e8 (they stay candidates, as in the reference), and the K best.
+ *   user_emb [n_users, D], item_emb [n_items, D]   fp32 row-major
+ *   test_users [n_test]                            dense user ids (int32)
+ *   train_indptr [n_users + 1] (int64), train_indices (int32, ascending inside a row): the training
+ *                                                  interaction matrix (Interaction.interaction_mat)
+ *   out_ids [n_test, K] (int32), out_scores [n_test, K]: best first
+ * Scores are DEFINED as the ascending-k fused multiply-add chain of fp32 products (the reference's BLAS
+ * summation order is unspecified); out_scores holds exactly those values.
+ * mode 0 ("exact"):    true top-K, score descending, ties by ascending item id, no duplicates.
+ * mode 1 ("refquirk"): find_k_largest as shipped, which visits the first K candidates twice, so an item
+ *                      with id < K that makes the list appears twice; K <= 64.
+ * engine 0: tcgen05 tensor path when D == 64 and K <= 64 (bf16 candidate generation with a proven error
+ *           bound, exact fp32 re-scoring of the candidates; results identical to engine 1), else SIMT.
+ * engine 1: SIMT fp32 brute force.   engine 2: tensor path or HGR_ERR_INVALID.
+ * stats (device uint64[4], optional, caller zeroes): candidates emitted by the tensor stage, candidates
+ * re-scored, users that overflowed to the brute-force fallback, reserved.
+ * ------------------------------------------------------------------------------------------- */
+size_t hgr_fullrank_topk_workspace_bytes(int64_t n_test, int64_t n_items, int32_t D, int32_t K, int32_t engine);
+int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *item_emb, int64_t n_items, int32_t D,
+                          const int32_t *test_users, int64_t n_test, const int64_t *train_indptr,
+                          const int32_t *train_indices, int32_t K, int32_t mode, int32_t engine, int32_t *out_ids,
+                          float *out_scores, uint64_t *stats, void *workspace, size_t workspace_bytes,
+                          hgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
