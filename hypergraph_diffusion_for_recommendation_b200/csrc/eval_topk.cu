@@ -11,20 +11,21 @@
 //   1. eval_pack_kernel      fp32 tables -> bf16 in the tcgen05 K-major no-swizzle core-matrix layout
 //                            (8 rows x 16 B core matrices; an 8-row group is 1 KB), row norms for the
 //                            error bound.  A tile is then ONE contiguous block: a single cp.async.bulk.
-//   2. eval_candidates_kernel  the dense step.  CTA = 256 test users x a range of item tiles (128 items).
-//                            warp 0: bulk-copy producer (4-stage mbarrier ring); warp 1: one thread issues
-//                            tcgen05.mma kind::f16 (bf16 x bf16 -> fp32, M128 N128 K16 x 4 per half) into
-//                            a double-buffered TMEM accumulator (2 stages x 2 halves x 128 columns = 512);
-//                            warps 2..9: epilogue, tcgen05.ld 32x32b (thread = user row), training items
-//                            poisoned to NaN from the train CSR row, running K-th-best threshold per user
-//                            kept in a sorted shared-memory list updated warp-cooperatively, elements above
-//                            (threshold - 2 eps) appended to the user's candidate list.  Scores never leave
-//                            the SM; only ~K ln(I/K) (score, id) pairs per user do.
-//   3. eval_rescore_kernel   exact fp32 re-scoring of the surviving candidates in the canonical order
-//                            (ascending-k fused multiply-add, oracle/hgr_oracle.c hgr_oracle_scores_f32) and
-//                            exact top-K: score descending, ties by ascending item id.  Because
-//                            |bf16 score - fp32 score| <= eps(user) is a proven bound, the candidate set is a
-//                            superset of the true top-K and the result is bit-identical to the oracle.
+//   2. eval_scores_kernel    the dense step, run twice.  CTA = 256 test users x a range of 128-item tiles.
+//                            warp 0: bulk-copy producer (6-stage mbarrier ring); warp 1: one thread issues
+//                            tcgen05.mma kind::f16 (bf16 x bf16 -> fp32, M128 N128 K16, 4 per half) into a
+//                            double-buffered TMEM accumulator (2 stages x 2 halves x 128 columns = 512);
+//                            warps 2..9: epilogue, tcgen05.ld 32x32b (thread = user row), the user's training
+//                            items poisoned to NaN by walking the train CSR row in step with the columns.
+//        SAMPLE pass         over 1/4 of the item tiles: 32 running bucket maxima per (user, item segment).
+//        eval_tau_kernel     K-th largest bucket maximum = a lower bound tau of the user's K-th best score.
+//        FILTER pass         over all item tiles: scores >= tau - 2 eps are appended to the user's candidate
+//                            list.  Scores never leave the SM; only ~(4 K + window) (score, id) pairs per user do.
+//   3. eval_rescore_kernel   approximate K-th best among the candidates prunes the list, the survivors are
+//                            re-scored exactly in fp32 in the canonical order (ascending-k fused multiply-add,
+//                            oracle/hgr_oracle.c hgr_oracle_scores_f32), exact top-K: score descending, ties by
+//                            ascending item id.  |bf16 score - fp32 score| <= eps(user) is a proven bound, so
+//                            the candidate set is a superset of the true top-K: bit-identical to the oracle.
 //   4. eval_brute_kernel     exact SIMT fallback for users whose candidate list overflowed (and the whole
 //                            job when D != 64 or K > 64): every score in fp32, K rounds of block arg-max.
 //   5. eval_refquirk_kernel  optional: replays find_k_largest's re-visit of the first K candidates
@@ -42,12 +43,15 @@ namespace hgr {
 constexpr int EV_D = 64;           // embedding width of the tensor path (one 128-byte bf16 row)
 constexpr int EV_BM = 256;         // users per CTA: two 128-row accumulators
 constexpr int EV_BN = 128;         // items per tile
-constexpr int EV_STAGES = 4;       // item tiles in flight
+constexpr int EV_STAGES = 6;       // item tiles in flight (also keeps the CTA above half an SM's shared memory:
+                                   // one CTA per SM, so its 512-column TMEM allocation never waits)
 constexpr int EV_A_BYTES = EV_BM * EV_D * 2;        // 32 KB
 constexpr int EV_B_BYTES = EV_BN * EV_D * 2;        // 16 KB
 constexpr int EV_EPI_WARPS = 8;
 constexpr int EV_THREADS = 64 + 32 * EV_EPI_WARPS;  // producer warp, MMA warp, 8 epilogue warps
 constexpr int EV_TMEM_COLS = 512;
+constexpr int EV_SAMPLE_STRIDE = 4;                 // the sample pass scores 1 / 4 of the item tiles
+constexpr int EV_BUCKETS = 32;                      // bucket maxima per (user, sample segment)
 constexpr float EV_MASK_SCORE = -10e8f;             // base/graph_recommender.py:80
 // |sum_k bf16(u_k) bf16(i_k) - fl32(sum_k u_k i_k)| <= EV_EPS_REL * ||u||_2 * ||i||_2 :
 // two bf16 roundings (2^-8 each, round to nearest) give (1 + 2^-8)^2 - 1 < 2^-7 (1 + 2^-9) per product,
@@ -55,18 +59,23 @@ constexpr float EV_MASK_SCORE = -10e8f;             // base/graph_recommender.py
 // 2 * 64 * 2^-23 of it.  0.0082 = 2^-7 * 1.05 covers all of it and the rounding of the norms themselves.
 constexpr float EV_EPS_REL = 0.0082f;
 
+enum { EV_SAMPLE = 0, EV_FILTER = 1 };
+
 struct EvalParams {
     const __nv_bfloat16 *Ap;  // packed test-user rows [n_test_pad / 8][8 chunks][8 rows][8]
     const __nv_bfloat16 *Bp;  // packed item rows      [n_items_pad / 8][...]
-    const float *slack;       // [n_test_pad] 2 * eps(user)
     const int32_t *test_users;
     const int64_t *train_indptr;
     const int32_t *train_indices;
-    float2 *cand;        // [n_splits][n_test_pad][cap] (approx score, item id bits)
+    float *bucket_max;   // SAMPLE out: [n_segments][n_test_pad][EV_BUCKETS]
+    const float *thr;    // FILTER in:  [n_test_pad] tau - 2 eps (-inf: no bound)
+    float2 *cand;        // FILTER out: [n_splits][n_test_pad][cap] (approx score, item id bits)
     int32_t *cand_cnt;   // [n_splits][n_test_pad]
-    float *cand_tau;     // [n_splits][n_test_pad] K-th best approx score seen by the split
-    int32_t *overflow;   // [n_test_pad]
-    int32_t n_test, n_items, n_tiles, tiles_per_split, cap, K;
+    int32_t *overflow;   // [n_test_pad] flag; [n_test_pad] = count, [n_test_pad + 1 ...] = list of flagged rows
+    int32_t n_test, n_items, n_tiles;
+    int32_t tiles_per_cta;  // tiles a CTA scores
+    int32_t tile_pitch;     // first tile of CTA y = y * tile_pitch
+    int32_t cap;
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -185,107 +194,70 @@ __global__ void eval_slack_kernel(float *__restrict__ slack, int64_t n, const un
     if (r < n) slack[r] = 2.0f * EV_EPS_REL * slack[r] * __uint_as_float(*max_norm_bits) + 1e-30f;
 }
 
-// ------------------------------------------------------------------------------------------ 2. candidates
+// ------------------------------------------------------------------------------------------ 2. scores
 struct EvalSmem {
     // offsets into dynamic shared memory (base aligned to 1024)
     static constexpr int A = 0;
     static constexpr int B = A + EV_A_BYTES;
-    static constexpr int LISTS = B + EV_STAGES * EV_B_BYTES;
+    static constexpr int END = B + EV_STAGES * EV_B_BYTES;
 };
 
-// Warp-cooperative handling of one 4-column group in which at least one lane (= user row) saw a value at or
-// above its threshold.  All 32 lanes work on one such row at a time: the row's sorted list of its K best
-// approximate scores lives in shared memory, one slot per lane (two when KPAD == 64).
-struct EvRowState {
-    float thr;  // running K-th best approximate score minus 2 eps; +inf for padding rows
-    int cnt;    // candidates appended so far
-};
-
-template <int KPAD>
-__device__ __noinline__ EvRowState eval_group_events(unsigned hits, float x0, float x1, float x2, float x3, int col, float thr,
-                                                     int cnt, float slack, float *__restrict__ lists,
-                                                     float2 *__restrict__ cand_rows, int32_t *__restrict__ overflow_rows,
-                                                     int n_items, int cap, int K) {
-    const int lane = threadIdx.x & 31;
-    while (hits) {
-        const int src = __ffs(hits) - 1;
-        hits &= hits - 1;
-        float y[4];
-        y[0] = __shfl_sync(0xffffffffu, x0, src);
-        y[1] = __shfl_sync(0xffffffffu, x1, src);
-        y[2] = __shfl_sync(0xffffffffu, x2, src);
-        y[3] = __shfl_sync(0xffffffffu, x3, src);
-        float thr_s = __shfl_sync(0xffffffffu, thr, src);
-        const float slack_s = __shfl_sync(0xffffffffu, slack, src);
-        int cnt_s = __shfl_sync(0xffffffffu, cnt, src);
-        float *list = lists + src * KPAD;
-        float2 *crow = cand_rows + (int64_t)src * cap;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float v = y[e];
-            const int c = col + e;
-            if (v >= thr_s && c < n_items) {  // warp-uniform
-                if (cnt_s < cap) {
-                    if (lane == 0) crow[cnt_s] = make_float2(v, __int_as_float(c));
-                } else if (lane == 0) {
-                    overflow_rows[src] = 1;
-                }
-                ++cnt_s;
-                if (KPAD == 32) {
-                    const float cur = list[lane];
-                    const int pos = __popc(__ballot_sync(0xffffffffu, cur >= v));
-                    if (pos < K) {
-                        const float up = __shfl_up_sync(0xffffffffu, cur, 1);
-                        const float nv = lane < pos ? cur : (lane == pos ? v : up);
-                        list[lane] = nv;
-                        thr_s = __shfl_sync(0xffffffffu, nv, K - 1) - slack_s;
-                    }
-                } else {
-                    const float c0 = list[lane], c1 = list[32 + lane];
-                    const int pos = __popc(__ballot_sync(0xffffffffu, c0 >= v)) + __popc(__ballot_sync(0xffffffffu, c1 >= v));
-                    if (pos < K) {
-                        const float u0 = __shfl_up_sync(0xffffffffu, c0, 1);
-                        float u1 = __shfl_up_sync(0xffffffffu, c1, 1);
-                        const float c31 = __shfl_sync(0xffffffffu, c0, 31);
-                        if (lane == 0) u1 = c31;
-                        const float n0 = lane < pos ? c0 : (lane == pos ? v : u0);
-                        const float n1 = (32 + lane) < pos ? c1 : ((32 + lane) == pos ? v : u1);
-                        list[lane] = n0;
-                        list[32 + lane] = n1;
-                        const float tau = (K <= 32) ? __shfl_sync(0xffffffffu, n0, (K - 1) & 31)
-                                                    : __shfl_sync(0xffffffffu, n1, (K - 33) & 31);
-                        thr_s = tau - slack_s;
-                    }
-                }
-            }
-        }
-        if (lane == src) {
-            thr = thr_s;
-            cnt = cnt_s;
-        }
+// Mark the user's training items (and, in the last tile, the padding columns) among columns
+// [col0, col0 + 32) as NaN: NaN never compares >= a threshold and fmaxf ignores it.  nt0 / nt1 are the next
+// two training items of the row (software-pipelined: the load of nt1 is in flight while nt0 is used).
+__device__ __forceinline__ void ev_poison(uint32_t (&v)[32], int col0, int n_items, int &nt0, int &nt1, int64_t &tp,
+                                          int64_t tend, const int32_t *__restrict__ train_indices) {
+    unsigned mb = 0;
+    if (nt0 < col0 + 32) {
+        do {
+            mb |= 1u << (nt0 - col0);
+            nt0 = nt1;
+            ++tp;
+            nt1 = tp + 1 < tend ? __ldg(train_indices + tp + 1) : INT_MAX;
+        } while (nt0 < col0 + 32);
     }
-    EvRowState out;
-    out.thr = thr;
-    out.cnt = cnt;
-    return out;
+    if (col0 + 32 > n_items) mb |= (col0 >= n_items) ? 0xffffffffu : (0xffffffffu << (n_items - col0));
+    if (mb) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (mb & (1u << j)) v[j] = 0x7fc00000u;
+    }
 }
 
-template <int KPAD>
-__global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const EvalParams P) {
+// Append the columns of one 4-column group that meet the user's threshold to the user's candidate list.
+__device__ __noinline__ int ev_append4(float x0, float x1, float x2, float x3, float thr, int col, int cnt, int cap,
+                                       float2 *__restrict__ crow) {
+    if (x0 >= thr) {
+        if (cnt < cap) crow[cnt] = make_float2(x0, __int_as_float(col));
+        ++cnt;
+    }
+    if (x1 >= thr) {
+        if (cnt < cap) crow[cnt] = make_float2(x1, __int_as_float(col + 1));
+        ++cnt;
+    }
+    if (x2 >= thr) {
+        if (cnt < cap) crow[cnt] = make_float2(x2, __int_as_float(col + 2));
+        ++cnt;
+    }
+    if (x3 >= thr) {
+        if (cnt < cap) crow[cnt] = make_float2(x3, __int_as_float(col + 3));
+        ++cnt;
+    }
+    return cnt;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalParams P) {
     extern __shared__ uint8_t ev_smem_raw[];
-    // 1024-byte aligned view of dynamic shared memory
     const uint32_t raw = smem_u32(ev_smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t *sm = ev_smem_raw + (base - raw);
-    float *lists_all = reinterpret_cast<float *>(sm + EvalSmem::LISTS);  // [8 warps][32 rows][KPAD]
+    const uint32_t base = (raw + 1023u) & ~1023u;  // 1024-byte aligned view of dynamic shared memory
     __shared__ __align__(8) uint64_t bars[2 * EV_STAGES + 1 + 4];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, split = blockIdx.y;
-    const int tile0 = split * P.tiles_per_split;
-    const int tile1 = min(tile0 + P.tiles_per_split, P.n_tiles);
-    const int n_my = tile1 - tile0;
+    const int m_blk = blockIdx.x, part = blockIdx.y;
+    const int tile0 = part * P.tile_pitch;
+    const int n_my = max(0, min(P.tiles_per_cta, P.n_tiles - tile0));
 
     const uint32_t bar_full = smem_u32(&bars[0]);               // [EV_STAGES]
     const uint32_t bar_empty = smem_u32(&bars[EV_STAGES]);      // [EV_STAGES]
@@ -310,10 +282,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const Ev
                      "r"((uint32_t)EV_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp >= 2) {  // every row's best-K list starts at -inf
-        float *l = lists_all + (warp - 2) * 32 * KPAD;
-        for (int j = lane; j < 32 * KPAD; j += 32) l[j] = -CUDART_INF_F;
     }
     tc_fence_before();
     __syncthreads();
@@ -367,18 +335,10 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const Ev
         const int ew = warp - 2;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
         const int half = ew >> 2;
-        const int row_in_cta = half * 128 + quad * 32 + lane;
-        const int64_t row = (int64_t)m_blk * EV_BM + row_in_cta;
+        const int64_t row = (int64_t)m_blk * EV_BM + half * 128 + quad * 32 + lane;
         const bool live = row < P.n_test;
         const int64_t n_pad = (int64_t)gridDim.x * EV_BM;
-        float *lists = lists_all + ew * 32 * KPAD;
-        // rows of this warp are consecutive: row - lane is lane 0's row
-        float2 *cand_rows = P.cand + ((int64_t)split * n_pad + (row - lane)) * P.cap;
-        int32_t *overflow_rows = P.overflow + (row - lane);
-        float thr = live ? -CUDART_INF_F : CUDART_INF_F;
-        const float slack = live ? P.slack[row] : 0.f;
-        int cnt = 0;
-        // training items of this user at or after the split's first column, walked in step with the columns
+        // training items of this user at or after the CTA's first column, walked in step with the columns
         int64_t tp = 0, tend = 0;
         if (live) {
             const int32_t u = P.test_users[row];
@@ -396,6 +356,17 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const Ev
         int nt0 = tp < tend ? __ldg(P.train_indices + tp) : INT_MAX;
         int nt1 = tp + 1 < tend ? __ldg(P.train_indices + tp + 1) : INT_MAX;
 
+        float bm[EV_BUCKETS];  // SAMPLE: running maxima, bucket = column mod 32
+#pragma unroll
+        for (int j = 0; j < EV_BUCKETS; ++j) bm[j] = -CUDART_INF_F;
+        float thr = CUDART_INF_F;  // FILTER: fixed threshold of this user
+        int cnt = 0;
+        float2 *crow = nullptr;
+        if (MODE == EV_FILTER) {
+            if (live) thr = P.thr[row];
+            crow = P.cand + ((int64_t)part * n_pad + row) * P.cap;
+        }
+
         for (int it = 0; it < n_my; ++it) {
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
@@ -403,35 +374,44 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const Ev
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + half * 128);
             const int col_tile = (tile0 + it) * EV_BN;
+            // two register buffers: the TMEM load of the next 32 columns is in flight while these are examined.
+            // The chunk loop is unrolled by 2 only: the body is large and an instruction-cache miss costs more
+            // than the loop overhead.
+            uint32_t va[32], vb[32];
+            tc_ld32(tcol, va);
 #pragma unroll 1
-            for (int c = 0; c < EV_BN / 32; ++c) {
-                uint32_t raw32[32];
-                tc_ld32(tcol + c * 32, raw32);
-                tc_ld_wait();
-                const int col0 = col_tile + c * 32;
-                if (nt0 < col0 + 32) {  // this user has training items among these 32 columns: poison them
-                    unsigned mb = 0;
-                    do {
-                        mb |= 1u << (nt0 - col0);
-                        nt0 = nt1;
-                        ++tp;
-                        nt1 = tp + 1 < tend ? __ldg(P.train_indices + tp + 1) : INT_MAX;
-                    } while (nt0 < col0 + 32);
+            for (int c2 = 0; c2 < EV_BN / 32; c2 += 2) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (mb & (1u << j)) raw32[j] = 0x7fc00000u;  // NaN: never >= a threshold, ignored by fmaxf
-                }
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t(&v)[32] = cc ? vb : va;
+                    uint32_t(&nx)[32] = cc ? va : vb;
+                    const int c = c2 + cc;
+                    tc_ld_wait();
+                    if (c + 1 < EV_BN / 32) tc_ld32(tcol + (c + 1) * 32, nx);
+                    const int col0 = col_tile + c * 32;
+                    if (nt0 < col0 + 32 || col0 + 32 > P.n_items)
+                        ev_poison(v, col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
+                    if (MODE == EV_SAMPLE) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float x0 = __uint_as_float(raw32[4 * g]), x1 = __uint_as_float(raw32[4 * g + 1]);
-                    const float x2 = __uint_as_float(raw32[4 * g + 2]), x3 = __uint_as_float(raw32[4 * g + 3]);
-                    const float m = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
-                    const unsigned hits = __ballot_sync(0xffffffffu, m >= thr);
-                    if (hits) {
-                        const EvRowState rs = eval_group_events<KPAD>(hits, x0, x1, x2, x3, col0 + 4 * g, thr, cnt, slack, lists,
-                                                                      cand_rows, overflow_rows, P.n_items, P.cap, P.K);
-                        thr = rs.thr;
-                        cnt = rs.cnt;
+                        for (int j = 0; j < 32; ++j) bm[j] = fmaxf(bm[j], __uint_as_float(v[j]));
+                    } else {
+                        // group maxima first: a user row meets its threshold in ~1 of 20 chunks, and then usually
+                        // in a single group of 4 columns
+                        float m4[8];
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            m4[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
+                                          fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+                        const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
+                                              fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+                        if (m >= thr) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                if (m4[g] >= thr)
+                                    cnt = ev_append4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                     __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]), thr,
+                                                     col0 + 4 * g, cnt, P.cap, crow);
+                        }
                     }
                 }
             }
@@ -439,10 +419,15 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_candidates_kernel(const Ev
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
         }
-        __syncwarp();
-        if (live) {
-            P.cand_cnt[(int64_t)split * n_pad + row] = min(cnt, P.cap);
-            P.cand_tau[(int64_t)split * n_pad + row] = lists[lane * KPAD + (P.K - 1)];
+        if (MODE == EV_SAMPLE) {
+            if (live) {
+                float4 *o = reinterpret_cast<float4 *>(P.bucket_max + ((int64_t)part * n_pad + row) * EV_BUCKETS);
+#pragma unroll
+                for (int j = 0; j < EV_BUCKETS / 4; ++j) o[j] = make_float4(bm[4 * j], bm[4 * j + 1], bm[4 * j + 2], bm[4 * j + 3]);
+            }
+        } else if (live) {
+            P.cand_cnt[(int64_t)part * n_pad + row] = min(cnt, P.cap);
+            if (cnt > P.cap && atomicExch(P.overflow + row, 1) == 0) P.overflow[n_pad + 1 + atomicAdd(P.overflow + n_pad, 1)] = (int32_t)row;
         }
     }
     tc_fence_before();
@@ -495,66 +480,130 @@ __device__ __forceinline__ bool is_train_item(const int32_t *__restrict__ a, int
     return lo < end && __ldg(a + lo) == v;
 }
 
+// ------------------------------------------------------------------------------------------ tau
+// One warp per test user: tau = K-th largest of the n_seg * 32 bucket maxima of the sample pass.  Every bucket
+// maximum is the score of a distinct unmasked item, so at least K items score >= tau: tau is a lower bound of
+// the user's K-th best approximate score.  Fewer than K non-empty buckets: no bound (-inf).
+// thr = tau - 2 eps with eps = EV_EPS_REL * ||u|| * max ||i|| (see EV_EPS_REL).
+__global__ void __launch_bounds__(128) eval_tau_kernel(const float *__restrict__ bucket_max, int n_seg, int64_t n_pad, int n_test,
+                                                       int K, const float *__restrict__ slack, float *__restrict__ thr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+    if (row >= n_test) return;
+    unsigned long long keys[16];  // n_seg <= 16 (make_plan)
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        keys[s] = 0ull;
+        if (s < n_seg) {
+            const float v = bucket_max[((int64_t)s * n_pad + row) * EV_BUCKETS + lane];
+            if (v > -CUDART_INF_F) keys[s] = rank_key(v, s * EV_BUCKETS + lane);  // false for NaN and for empty buckets
+        }
+    }
+    unsigned long long prev = ~0ull, best = 0ull;
+    for (int r = 0; r < K; ++r) {
+        best = 0ull;
+#pragma unroll
+        for (int s = 0; s < 16; ++s)
+            if (keys[s] < prev && keys[s] > best) best = keys[s];
+        best = warp_max_u64(best);
+        if (best == 0ull) break;
+        prev = best;
+    }
+    if (lane == 0) {
+        float tau = -CUDART_INF_F;
+        if (best != 0ull) {
+            const uint32_t ob = (uint32_t)(best >> 32);
+            tau = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+        }
+        thr[row] = tau - slack[row];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ 3. rescore
 constexpr int RS_WARPS = 4;
-constexpr int RS_CAP = 512;  // surviving candidates per user kept in shared memory
+constexpr int RS_CAP = 1024;  // candidates of one user held in shared memory
 
+// One warp per test user.  (a) the candidates' approximate scores give the approximate K-th best tau_a;
+// (b) candidates below tau_a - 2 eps cannot be in the exact top-K and are dropped; (c) the survivors are
+// re-scored exactly; (d) K rounds of warp arg-max on (score desc, id asc) keys.
 __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
     const float *__restrict__ user_emb, const float *__restrict__ item_emb, int D, const int32_t *__restrict__ test_users,
     const int64_t *__restrict__ train_indptr, const int32_t *__restrict__ train_indices, const float2 *__restrict__ cand,
-    const int32_t *__restrict__ cand_cnt, const float *__restrict__ cand_tau, const float *__restrict__ slack,
-    int32_t *__restrict__ overflow, int n_splits, int64_t n_pad, int cap, int n_test, int K, int32_t *__restrict__ out_ids,
-    float *__restrict__ out_scores, unsigned long long *__restrict__ stats) {
+    const int32_t *__restrict__ cand_cnt, const float *__restrict__ slack, int32_t *__restrict__ overflow, int n_splits,
+    int64_t n_pad, int cap, int n_test, int K, int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+    unsigned long long *__restrict__ stats) {
     __shared__ float u_sm[RS_WARPS][128];
     __shared__ unsigned long long keys[RS_WARPS][RS_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
     if (row >= n_test) return;
     if (overflow[row]) return;  // handled by eval_brute_kernel
+    int n_c = 0;
+    for (int s = 0; s < n_splits; ++s) n_c += cand_cnt[(int64_t)s * n_pad + row];
+    if (n_c > RS_CAP) {
+        if (lane == 0 && atomicExch(overflow + row, 1) == 0) overflow[n_pad + 1 + atomicAdd(overflow + n_pad, 1)] = (int32_t)row;
+        return;
+    }
     const int32_t u = test_users[row];
     for (int k = lane; k < D; k += 32) u_sm[warp][k] = user_emb[(int64_t)u * D + k];
-    // a split's K-th best approximate score bounds the global K-th best from below
-    float tau = -CUDART_INF_F;
-    for (int s = 0; s < n_splits; ++s) tau = fmaxf(tau, cand_tau[(int64_t)s * n_pad + row]);
-    const float keep = tau - slack[row];
-    __syncwarp();
-    int n_keep = 0;
-    unsigned long long seen = 0;
+    // (a) approximate keys into shared memory
+    int base = 0;
     for (int s = 0; s < n_splits; ++s) {
         const int cnt = cand_cnt[(int64_t)s * n_pad + row];
         const float2 *crow = cand + ((int64_t)s * n_pad + row) * cap;
-        seen += (unsigned long long)cnt;
-        for (int j0 = 0; j0 < cnt; j0 += 32) {
-            const int j = j0 + lane;
-            bool ok = false;
-            int id = 0;
-            float sc = 0.f;
-            if (j < cnt) {
-                const float2 c = crow[j];
-                id = __float_as_int(c.y);
-                ok = c.x >= keep;
-                if (ok) sc = exact_score(u_sm[warp], item_emb + (int64_t)id * D, D);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const int slot = n_keep + __popc(m & ((1u << lane) - 1u));
-            if (ok && slot < RS_CAP) keys[warp][slot] = rank_key(sc, id);
-            n_keep += __popc(m);
+        for (int j = lane; j < cnt; j += 32) {
+            const float2 c = crow[j];
+            keys[warp][base + j] = rank_key(c.x, __float_as_int(c.y));
         }
-    }
-    if (n_keep > RS_CAP) {  // cannot happen with sane thresholds; route the row to the exact fallback
-        if (lane == 0) overflow[row] = 1;
-        return;
+        base += cnt;
     }
     __syncwarp();
+    unsigned long long prev = ~0ull, best = 0ull;
+    for (int r = 0; r < K; ++r) {
+        best = 0ull;
+        for (int j = lane; j < n_c; j += 32) {
+            const unsigned long long k = keys[warp][j];
+            if (k < prev && k > best) best = k;
+        }
+        best = warp_max_u64(best);
+        if (best == 0ull) break;
+        prev = best;
+    }
+    // (b) + (c): keep keys >= (tau_a - 2 eps), re-score them, compact in place (slot <= source index)
+    unsigned long long keep_key = 0ull;
+    if (best != 0ull) {
+        const uint32_t ob = (uint32_t)(best >> 32);
+        const float tau_a = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+        keep_key = (unsigned long long)orderable(tau_a - slack[row]) << 32;
+    }
+    int n_keep = 0;
+    for (int j0 = 0; j0 < n_c; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        unsigned long long nk = 0ull;
+        if (j < n_c) {
+            const unsigned long long k = keys[warp][j];
+            ok = k >= keep_key;
+            if (ok) {
+                const int id = (int32_t)(0xffffffffu - (uint32_t)(k & 0xffffffffu));
+                nk = rank_key(exact_score(u_sm[warp], item_emb + (int64_t)id * D, D), id);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        __syncwarp();
+        if (ok) keys[warp][n_keep + __popc(m & ((1u << lane) - 1u))] = nk;
+        n_keep += __popc(m);
+        __syncwarp();
+    }
     if (lane == 0 && stats) {
-        atomicAdd(stats + 0, seen);
+        atomicAdd(stats + 0, (unsigned long long)n_c);
         atomicAdd(stats + 1, (unsigned long long)n_keep);
     }
-    // K rounds: best key strictly below the previous winner
-    unsigned long long prev = ~0ull;
+    // (d) K rounds: best exact key strictly below the previous winner
+    prev = ~0ull;
     int filled = 0;
     for (int r = 0; r < K; ++r) {
-        unsigned long long best = 0ull;
+        best = 0ull;
         for (int j = lane; j < n_keep; j += 32) {
             const unsigned long long k = keys[warp][j];
             if (k < prev && k > best) best = k;
@@ -564,9 +613,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
         prev = best;
         if (lane == 0) {
             const uint32_t ob = (uint32_t)(best >> 32);
-            const uint32_t fb = (ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob;
             out_ids[row * K + r] = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffu));
-            out_scores[row * K + r] = __uint_as_float(fb);
+            out_scores[row * K + r] = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
         }
         ++filled;
     }
@@ -592,7 +640,7 @@ __global__ void __launch_bounds__(BF_THREADS) eval_brute_kernel(const float *__r
                                                                 const int64_t *__restrict__ train_indptr,
                                                                 const int32_t *__restrict__ train_indices,
                                                                 const int32_t *__restrict__ overflow, int only_overflow,
-                                                                int n_test, int K, float *__restrict__ scratch,
+                                                                int64_t n_pad, int n_test, int K, float *__restrict__ scratch,
                                                                 int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
                                                                 unsigned long long *__restrict__ stats) {
     __shared__ float u_sm[128];
@@ -600,8 +648,9 @@ __global__ void __launch_bounds__(BF_THREADS) eval_brute_kernel(const float *__r
     __shared__ unsigned long long winner;
     float *srow = scratch + (int64_t)blockIdx.x * n_items;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int row = blockIdx.x; row < n_test; row += gridDim.x) {
-        if (only_overflow && !overflow[row]) continue;
+    const int n_rows = only_overflow ? overflow[n_pad] : n_test;
+    for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
+        const int row = only_overflow ? overflow[n_pad + 1 + q] : q;
         const int32_t u = test_users[row];
         __syncthreads();
         for (int k = threadIdx.x; k < D; k += BF_THREADS) u_sm[k] = user_emb[(int64_t)u * D + k];
@@ -700,8 +749,10 @@ __global__ void __launch_bounds__(128) eval_refquirk_kernel(const float *__restr
 // ------------------------------------------------------------------------------------------ host side
 struct EvalPlan {
     int64_t n_test_pad, n_items_pad;
-    int n_tiles, n_splits, tiles_per_split, cap, kpad, n_brute_blocks;
-    size_t off_ap, off_bp, off_slack, off_maxnorm, off_cand, off_cnt, off_tau, off_overflow, off_scratch, total;
+    int n_tiles, cap, n_brute_blocks;
+    int n_seg, seg_tiles, seg_pitch;         // sample pass: segment y scores tiles [y * seg_pitch, + seg_tiles)
+    int n_splits, tiles_per_split;           // filter pass
+    size_t off_ap, off_bp, off_slack, off_maxnorm, off_bucket, off_thr, off_cand, off_cnt, off_overflow, off_scratch, total;
     bool tensor;
 };
 
@@ -714,10 +765,9 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
     p.n_test_pad = ceil_div(n_test > 0 ? n_test : 1, EV_BM) * EV_BM;
     p.n_items_pad = ceil_div(n_items > 0 ? n_items : 1, EV_BN) * EV_BN;
     p.n_tiles = (int)(p.n_items_pad / EV_BN);
-    p.kpad = K <= 32 ? 32 : 64;
     p.cap = K <= 32 ? 512 : 1024;
-    // enough CTAs to fill 148 SMs about twice, but never fewer than 8 tiles per split
     const int64_t m_blocks = p.n_test_pad / EV_BM;
+    // filter pass: enough CTAs to fill 148 SMs about twice, at least 8 tiles per CTA
     int splits = (int)ceil_div(2 * 148, m_blocks);
     const int max_splits = p.n_tiles / 8 > 0 ? p.n_tiles / 8 : 1;
     if (splits > max_splits) splits = max_splits;
@@ -725,6 +775,15 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
     if (splits < 1) splits = 1;
     p.tiles_per_split = (int)ceil_div(p.n_tiles, splits);
     p.n_splits = (int)ceil_div(p.n_tiles, p.tiles_per_split);
+    // sample pass: n_seg contiguous segments spread evenly over the catalogue, together 1 / EV_SAMPLE_STRIDE of it;
+    // at least 4 segments (128 buckets >= K), more when few user blocks would leave SMs idle
+    int seg = (int)ceil_div(2 * 148, m_blocks);
+    if (seg < 4) seg = 4;
+    if (seg > 16) seg = 16;
+    if (seg > p.n_tiles) seg = p.n_tiles;
+    p.seg_pitch = p.n_tiles / seg;
+    p.n_seg = seg;
+    p.seg_tiles = (int)ceil_div(p.seg_pitch, EV_SAMPLE_STRIDE);
     p.n_brute_blocks = p.tensor ? 148 : 148 * 4;
     if (p.n_brute_blocks > n_test && n_test > 0) p.n_brute_blocks = (int)n_test;
     size_t o = 0;
@@ -733,11 +792,12 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
         p.off_bp = o; o = align_up(o + (size_t)p.n_items_pad * EV_D * 2, 256);
         p.off_slack = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
         p.off_maxnorm = o; o = align_up(o + 256, 256);
+        p.off_bucket = o; o = align_up(o + (size_t)p.n_seg * p.n_test_pad * EV_BUCKETS * 4, 256);
+        p.off_thr = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
         p.off_cand = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * p.cap * 8, 256);
         p.off_cnt = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * 4, 256);
-        p.off_tau = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * 4, 256);
     }
-    p.off_overflow = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
+    p.off_overflow = o; o = align_up(o + (size_t)(2 * p.n_test_pad + 1) * 4, 256);
     p.off_scratch = o; o = align_up(o + (size_t)p.n_brute_blocks * (size_t)(n_items > 0 ? n_items : 1) * 4, 256);
     p.total = o;
     return p;
@@ -778,12 +838,13 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
     int32_t *overflow = reinterpret_cast<int32_t *>(ws + p.off_overflow);
     float *scratch = reinterpret_cast<float *>(ws + p.off_scratch);
     unsigned long long *st64 = reinterpret_cast<unsigned long long *>(stats);
-    HGR_CUDA_OK(cudaMemsetAsync(overflow, 0, (size_t)p.n_test_pad * 4, st));
+    HGR_CUDA_OK(cudaMemsetAsync(overflow, 0, (size_t)(p.n_test_pad + 1) * 4, st));
 
     if (p.tensor) {
         __nv_bfloat16 *Ap = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_ap);
         __nv_bfloat16 *Bp = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_bp);
         float *slack = reinterpret_cast<float *>(ws + p.off_slack);
+        float *thr = reinterpret_cast<float *>(ws + p.off_thr);
         unsigned int *maxnorm = reinterpret_cast<unsigned int *>(ws + p.off_maxnorm);
         HGR_CUDA_OK(cudaMemsetAsync(maxnorm, 0, 4, st));
         eval_pack_kernel<<<(unsigned)ceil_div(p.n_items_pad * 8, 256), 256, 0, st>>>(item_emb, nullptr, n_items, p.n_items_pad,
@@ -796,40 +857,47 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
         HGR_LAUNCH_OK("eval_slack_kernel");
 
         EvalParams P;
+        memset(&P, 0, sizeof(P));
         P.Ap = Ap;
         P.Bp = Bp;
-        P.slack = slack;
         P.test_users = test_users;
         P.train_indptr = train_indptr;
         P.train_indices = train_indices;
+        P.bucket_max = reinterpret_cast<float *>(ws + p.off_bucket);
+        P.thr = thr;
         P.cand = reinterpret_cast<float2 *>(ws + p.off_cand);
         P.cand_cnt = reinterpret_cast<int32_t *>(ws + p.off_cnt);
-        P.cand_tau = reinterpret_cast<float *>(ws + p.off_tau);
         P.overflow = overflow;
         P.n_test = (int32_t)n_test;
         P.n_items = (int32_t)n_items;
         P.n_tiles = p.n_tiles;
-        P.tiles_per_split = p.tiles_per_split;
         P.cap = p.cap;
-        P.K = K;
-        const size_t smem = 1024 + (size_t)EvalSmem::LISTS + (size_t)EV_EPI_WARPS * 32 * p.kpad * 4;
-        const dim3 grid((unsigned)(p.n_test_pad / EV_BM), (unsigned)p.n_splits);
-        if (p.kpad == 32) {
-            HGR_CUDA_OK(cudaFuncSetAttribute(eval_candidates_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            eval_candidates_kernel<32><<<grid, EV_THREADS, smem, st>>>(P);
-        } else {
-            HGR_CUDA_OK(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            eval_candidates_kernel<64><<<grid, EV_THREADS, smem, st>>>(P);
+        const size_t smem = 1024 + (size_t)EvalSmem::END;
+        static bool attr_done = false;
+        if (!attr_done) {
+            HGR_CUDA_OK(cudaFuncSetAttribute(eval_scores_kernel<EV_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HGR_CUDA_OK(cudaFuncSetAttribute(eval_scores_kernel<EV_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
         }
-        HGR_LAUNCH_OK("eval_candidates_kernel");
+        const unsigned m_blocks = (unsigned)(p.n_test_pad / EV_BM);
+        P.tiles_per_cta = p.seg_tiles;
+        P.tile_pitch = p.seg_pitch;
+        eval_scores_kernel<EV_SAMPLE><<<dim3(m_blocks, (unsigned)p.n_seg), EV_THREADS, smem, st>>>(P);
+        HGR_LAUNCH_OK("eval_scores_kernel<sample>");
+        eval_tau_kernel<<<(unsigned)ceil_div(n_test, 4), 128, 0, st>>>(P.bucket_max, p.n_seg, p.n_test_pad, (int)n_test, K, slack, thr);
+        HGR_LAUNCH_OK("eval_tau_kernel");
+        P.tiles_per_cta = p.tiles_per_split;
+        P.tile_pitch = p.tiles_per_split;
+        eval_scores_kernel<EV_FILTER><<<dim3(m_blocks, (unsigned)p.n_splits), EV_THREADS, smem, st>>>(P);
+        HGR_LAUNCH_OK("eval_scores_kernel<filter>");
         eval_rescore_kernel<<<(unsigned)ceil_div(n_test, RS_WARPS), RS_WARPS * 32, 0, st>>>(
-            user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, P.cand_tau, slack, overflow,
-            p.n_splits, p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
+            user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, slack, overflow, p.n_splits,
+            p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
         HGR_LAUNCH_OK("eval_rescore_kernel");
     }
     eval_brute_kernel<<<(unsigned)p.n_brute_blocks, BF_THREADS, 0, st>>>(user_emb, item_emb, D, (int)n_items, test_users,
                                                                         train_indptr, train_indices, overflow, p.tensor ? 1 : 0,
-                                                                        (int)n_test, K, scratch, out_ids, out_scores, st64);
+                                                                        p.n_test_pad, (int)n_test, K, scratch, out_ids, out_scores, st64);
     HGR_LAUNCH_OK("eval_brute_kernel");
     if (mode == 1) {
         eval_refquirk_kernel<<<(unsigned)ceil_div(n_test, 4), 128, 0, st>>>(user_emb, item_emb, D, test_users, train_indptr,
