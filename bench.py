@@ -211,11 +211,12 @@ def run_ours(args):
     U, I, E, B = workload_dims(args.workload, world)
     small = not WORKLOADS[args.workload][4]
     u, i = powerlaw_interactions_device(U, I, E, dev, seed=1234)
+    part = None
     if world > 1:
         from hypergraph_diffusion_for_recommendation_b200 import dist as hdist
 
         ctx = hdist.build_partitioned(u, i, U, I, rank, world, dev)
-        data, adj = ctx.data, ctx.adj
+        data, adj, part = ctx.data, ctx.adj, ctx.part
     else:
         adj = norm_adj_from_pairs_torch(u, i, U, I)
         data = types.SimpleNamespace(n_users=U, n_items=I, norm_adj=None, norm_adj_device=adj)
@@ -232,8 +233,8 @@ def run_ours(args):
     # "next" row of SURVEY.md 8f; parity runs replay the reference sampler's triples instead)
     n_steps = args.warmup + args.steps
     gen = torch.Generator(device=dev)
-    gen.manual_seed(99 + rank)
-    b_local = B // world
+    gen.manual_seed(99)  # the same batch on every rank: the sharded step evaluates the loss on the whole batch (dist.py)
+    b_local = B
     host_triples, dev_triples = [], []
     for s in range(n_steps):
         pick = torch.randint(0, int(u.numel()), (b_local,), device=dev, generator=gen)
@@ -241,6 +242,7 @@ def run_ours(args):
         tn = torch.randint(0, I, (b_local,), device=dev, generator=gen)
         dev_triples.append((tu, tp, tn))
         host_triples.append(tuple(t.cpu().pin_memory() for t in (tu, tp, tn)))
+    eval_inputs = build_eval_inputs(u, i, U, I, part, rank, dev)
     del u, i
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
 
@@ -253,6 +255,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step(tri):
+        if world > 1:
+            return hdist.train_step(model, optimizer, adj, tri[0], tri[1], tri[2], REG, B)
         return trainer.train_step(model, optimizer, tri[0], tri[1], tri[2], REG, B)
 
     def timed(kind):
@@ -298,9 +302,17 @@ def run_ours(args):
 
     clocks = ClockSampler(local_rank)
     clocks.start()
+    if world > 1:
+        adj.gather_events = []
     total_ms, losses, launches = timed("device")
     clock_info = clocks.stop()
+    gather_ms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        gather_ms = sum(a.elapsed_time(b) for a, b in adj.gather_events) / args.steps
+        adj.gather_events = None
     e2e_ms, _, _ = timed("e2e")
+    eval_info = run_eval(model, eval_inputs, part, adj, world, rank, dev, barrier)
 
     ms_per_step = total_ms / args.steps
     steps_per_epoch = math.ceil(E / B)
@@ -312,7 +324,7 @@ def run_ours(args):
     spmm_total_ms = sum(a.elapsed_time(b) for a, b, _ in spmm_events)
     spmm_ms = [spmm_total_ms / max(sum(c for _, _, c in spmm_events), 1)] * sum(c for _, _, c in spmm_events)
     peak, peak_src = measured_peaks()
-    n_rows, n_cols = adj.shape
+    n_rows, n_cols = (adj.block if world > 1 else adj).shape  # the rank's block of rows when sharded
     alg = spmm_algorithmic_bytes(n_rows, n_cols, nnz, D)
     avg_ms = sum(spmm_ms) / max(len(spmm_ms), 1)
     achieved = alg / (avg_ms * 1e-3) / 1e9 if spmm_ms else None
@@ -339,11 +351,78 @@ def run_ours(args):
             "e2e": {"value": e2e_epoch_s, "unit": "s", "h2d_bytes_per_step": 3 * 8 * b_local, "d2h_bytes_per_step": 8,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+            "eval": eval_info, "allgather_ms_per_step": gather_ms,
             "loss": [float(x) for x in losses.tolist()],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+EVAL_K = 20
+EVAL_MAX_USERS = 262_144  # test users ranked per GPU in the bench (all of them when the shape has fewer)
+
+
+def build_eval_inputs(u, i, U, I, part, rank, dev):
+    """Training matrix rows (the mask) of the users this rank evaluates, as CSR over local user ids."""
+    import torch
+
+    u0, u1 = (0, U) if part is None else part.users_of(rank)
+    n_own = min(u1 - u0, EVAL_MAX_USERS)
+    m = (u >= u0) & (u < u0 + n_own)
+    key = torch.sort((u[m].to(torch.int64) - u0) * I + i[m].to(torch.int64)).values
+    indptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.bincount(torch.div(key, I, rounding_mode="floor"), minlength=n_own), 0, out=indptr[1:])
+    return {"n_own": n_own, "indptr": indptr, "indices": (key % I).to(torch.int32), "n_items": I}
+
+
+def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
+    """Full-ranking evaluation sharded by user: every rank ranks its own users against the whole item table
+    (gathered once), top-EVAL_K with the training items masked.  users/s = users of all ranks / max time."""
+    import torch
+    import torch.distributed as dist
+
+    from hypergraph_diffusion_for_recommendation_b200 import evaluation as E
+
+    with torch.no_grad():
+        out_u, out_i = model()[:2]
+        if world > 1:
+            full = adj.all_gather(torch.cat([out_u, out_i], 0))
+            item_tab = full[part.perm_item(torch.arange(ev["n_items"], device=dev))].contiguous()
+            del full
+        else:
+            item_tab = out_i.contiguous()
+        user_tab = out_u[:ev["n_own"]].contiguous()
+        users = torch.arange(ev["n_own"], device=dev, dtype=torch.int32)
+        times, stats = [], None
+        for it in range(iters + 1):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ids, sc, stats = E.fullrank_topk(user_tab, item_tab, users, ev["indptr"], ev["indices"], EVAL_K, mode="exact",
+                                             engine="auto", return_stats=True)
+            host_ids = ids.cpu()  # the [n_test, K] id matrix is what the reference's metric code consumes
+            e1.record()
+            torch.cuda.synchronize()
+            if it > 0:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        n_users_total = ev["n_own"]
+        if world > 1:
+            t = torch.tensor([ms, float(ev["n_own"])], device=dev, dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, n_users_total = float(tmax[0]), int(t[1])
+        s = stats.tolist()
+        flops = 2.0 * D * ev["n_items"] * n_users_total
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf = flops / (ms * 1e-3) / 1e12
+        return {"users_per_s": n_users_total / ms * 1e3, "ms": ms, "users": n_users_total, "items": ev["n_items"], "k": EVAL_K,
+                "mode": "exact", "d2h_bytes": int(host_ids.numel() * 4), "score_tflops": tf,
+                "tensor_frac_of_measured_bf16": tf / (peaks.get("bf16_tflops", 1590.0) * world),
+                "candidates_per_user": s[0] / max(ev["n_own"], 1), "rescored_per_user": s[1] / max(ev["n_own"], 1),
+                "fallback_users": s[2]}
 
 
 def main():

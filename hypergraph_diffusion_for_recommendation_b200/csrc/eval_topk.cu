@@ -8,7 +8,7 @@
 // i.e. one GEMV + a PCIe copy of n_items floats + a python mask loop + a numba insertion top-K per user.
 //
 // Pipeline (all on the caller's stream, no host synchronisation):
-//   1. eval_pack_kernel      fp32 tables -> bf16 in the tcgen05 K-major no-swizzle core-matrix layout
+//   1. eval_pack_kernel      fp32 tables -> two bf16 terms (hi + lo, 16 significant bits) in the tcgen05 K-major no-swizzle core-matrix layout
 //                            (8 rows x 16 B core matrices; an 8-row group is 1 KB), row norms for the
 //                            error bound.  A tile is then ONE contiguous block: a single cp.async.bulk.
 //   2. eval_scores_kernel    the dense step, run twice.  CTA = 256 test users x a range of 128-item tiles.
@@ -43,27 +43,32 @@ namespace hgr {
 constexpr int EV_D = 64;           // embedding width of the tensor path (one 128-byte bf16 row)
 constexpr int EV_BM = 256;         // users per CTA: two 128-row accumulators
 constexpr int EV_BN = 128;         // items per tile
-constexpr int EV_STAGES = 6;       // item tiles in flight (also keeps the CTA above half an SM's shared memory:
-                                   // one CTA per SM, so its 512-column TMEM allocation never waits)
-constexpr int EV_A_BYTES = EV_BM * EV_D * 2;        // 32 KB
-constexpr int EV_B_BYTES = EV_BN * EV_D * 2;        // 16 KB
+constexpr int EV_STAGES = 4;       // item tiles in flight (192 KB of shared memory: one CTA per SM, so its
+                                   // 512-column TMEM allocation never waits)
+constexpr int EV_A_BYTES = EV_BM * EV_D * 2;        // 32 KB per bf16 term (hi, lo)
+constexpr int EV_B_BYTES = EV_BN * EV_D * 2;        // 16 KB per bf16 term (hi, lo)
 constexpr int EV_EPI_WARPS = 8;
 constexpr int EV_THREADS = 64 + 32 * EV_EPI_WARPS;  // producer warp, MMA warp, 8 epilogue warps
 constexpr int EV_TMEM_COLS = 512;
 constexpr int EV_SAMPLE_STRIDE = 4;                 // the sample pass scores 1 / 4 of the item tiles
 constexpr int EV_BUCKETS = 32;                      // bucket maxima per (user, sample segment)
 constexpr float EV_MASK_SCORE = -10e8f;             // base/graph_recommender.py:80
-// |sum_k bf16(u_k) bf16(i_k) - fl32(sum_k u_k i_k)| <= EV_EPS_REL * ||u||_2 * ||i||_2 :
-// two bf16 roundings (2^-8 each, round to nearest) give (1 + 2^-8)^2 - 1 < 2^-7 (1 + 2^-9) per product,
-// Cauchy-Schwarz turns sum |u_k i_k| into the norm product, and the two fp32 accumulations add at most
-// 2 * 64 * 2^-23 of it.  0.0082 = 2^-7 * 1.05 covers all of it and the rounding of the norms themselves.
-constexpr float EV_EPS_REL = 0.0082f;
+// Every fp32 value x is split into two bf16 terms, hi = bf16(x) and lo = bf16(x - hi), so |x - hi - lo| <= 2^-16 |x|,
+// and the tensor cores accumulate  hi.lo + lo.hi + hi.hi  (three K = 64 products per tile) in fp32.  Error against the
+// canonical fp32 score, relative to sum_k |u_k i_k| <= ||u||_2 ||i||_2 (Cauchy-Schwarz):
+//   dropped terms (lo.lo and the two residuals)                      <= 3 * 2^-16 * (1 + 2^-7)      = 4.6e-5
+//   fp32 accumulation of 12 chained K = 16 MMAs (17 addends each, truncating alignment, 2^-23)  <= 2.5e-5
+//   the canonical fp32 chain itself (64 fused multiply-adds, 2^-24)                               <= 0.4e-5
+// EV_EPS_REL = 1e-4 covers their sum (7.5e-5) and the rounding of the norms.  eval_rescore_kernel measures the
+// largest |approx - exact| / (EV_EPS_REL ||u|| max||i||) it sees into stats[3] (parts per million): tests assert < 1e6.
+constexpr float EV_EPS_REL = 1.0e-4f;
 
 enum { EV_SAMPLE = 0, EV_FILTER = 1 };
 
 struct EvalParams {
-    const __nv_bfloat16 *Ap;  // packed test-user rows [n_test_pad / 8][8 chunks][8 rows][8]
-    const __nv_bfloat16 *Bp;  // packed item rows      [n_items_pad / 8][...]
+    const __nv_bfloat16 *Ap;  // packed test-user rows, [2 terms: hi, lo][n_test_pad / 8][8 chunks][8 rows][8]
+    const __nv_bfloat16 *Bp;  // packed item rows,      [2 terms: hi, lo][n_items_pad / 8][...]
+    int64_t a_term_stride, b_term_stride;  // bytes between the hi and the lo array
     const int32_t *test_users;
     const int64_t *train_indptr;
     const int32_t *train_indices;
@@ -170,13 +175,16 @@ __global__ void __launch_bounds__(256) eval_pack_kernel(const float *__restrict_
             b = __ldg(p + 1);
         }
     }
-    __nv_bfloat162 q[4];
-    q[0] = __floats2bfloat162_rn(a.x, a.y);
-    q[1] = __floats2bfloat162_rn(a.z, a.w);
-    q[2] = __floats2bfloat162_rn(b.x, b.y);
-    q[3] = __floats2bfloat162_rn(b.z, b.w);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        hi[j] = __float2bfloat16_rn(x[j]);
+        lo[j] = __float2bfloat16_rn(x[j] - __bfloat162float(hi[j]));
+    }
     const int64_t off = (row >> 3) * 512 + chunk * 64 + (row & 7) * 8;  // in bf16 elements
-    *reinterpret_cast<uint4 *>(out + off) = *reinterpret_cast<const uint4 *>(q);
+    *reinterpret_cast<uint4 *>(out + off) = *reinterpret_cast<const uint4 *>(hi);
+    *reinterpret_cast<uint4 *>(out + n_rows_pad * EV_D + off) = *reinterpret_cast<const uint4 *>(lo);
     float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w) + (b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w);
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     ss += __shfl_xor_sync(0xffffffffu, ss, 2);
@@ -197,9 +205,9 @@ __global__ void eval_slack_kernel(float *__restrict__ slack, int64_t n, const un
 // ------------------------------------------------------------------------------------------ 2. scores
 struct EvalSmem {
     // offsets into dynamic shared memory (base aligned to 1024)
-    static constexpr int A = 0;
-    static constexpr int B = A + EV_A_BYTES;
-    static constexpr int END = B + EV_STAGES * EV_B_BYTES;
+    static constexpr int A = 0;                      // [hi 32 KB | lo 32 KB]
+    static constexpr int B = A + 2 * EV_A_BYTES;     // per stage [hi 16 KB | lo 16 KB]
+    static constexpr int END = B + EV_STAGES * 2 * EV_B_BYTES;
 };
 
 // Mark the user's training items (and, in the last tile, the padding columns) among columns
@@ -289,19 +297,22 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        // ===== producer: one 32 KB bulk copy for the user block, one 16 KB bulk copy per item tile =====
+        // ===== producer: two 32 KB bulk copies for the user block (hi, lo), two 16 KB bulk copies per item tile =====
         if (lane == 0 && n_my > 0) {
-            mbar_arrive_expect_tx(bar_a, EV_A_BYTES);
-            bulk_copy_g2s(base + EvalSmem::A, reinterpret_cast<const uint8_t *>(P.Ap) + (int64_t)m_blk * EV_A_BYTES, EV_A_BYTES,
-                          bar_a);
+            const uint8_t *a_src = reinterpret_cast<const uint8_t *>(P.Ap) + (int64_t)m_blk * EV_A_BYTES;
+            const uint8_t *b_src = reinterpret_cast<const uint8_t *>(P.Bp);
+            mbar_arrive_expect_tx(bar_a, 2 * EV_A_BYTES);
+            bulk_copy_g2s(base + EvalSmem::A, a_src, EV_A_BYTES, bar_a);
+            bulk_copy_g2s(base + EvalSmem::A + EV_A_BYTES, a_src + P.a_term_stride, EV_A_BYTES, bar_a);
             for (int it = 0; it < n_my; ++it) {
                 const int s = it % EV_STAGES;
                 const uint32_t ph = (it / EV_STAGES) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                mbar_arrive_expect_tx(bar_full + 8 * s, EV_B_BYTES);
-                bulk_copy_g2s(base + EvalSmem::B + s * EV_B_BYTES,
-                              reinterpret_cast<const uint8_t *>(P.Bp) + (int64_t)(tile0 + it) * EV_B_BYTES, EV_B_BYTES,
-                              bar_full + 8 * s);
+                mbar_arrive_expect_tx(bar_full + 8 * s, 2 * EV_B_BYTES);
+                const uint32_t dst = base + EvalSmem::B + s * 2 * EV_B_BYTES;
+                const uint8_t *src = b_src + (int64_t)(tile0 + it) * EV_B_BYTES;
+                bulk_copy_g2s(dst, src, EV_B_BYTES, bar_full + 8 * s);
+                bulk_copy_g2s(dst + EV_B_BYTES, src + P.b_term_stride, EV_B_BYTES, bar_full + 8 * s);
             }
         }
     } else if (warp == 1) {
@@ -319,11 +330,16 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t d = tmem_base + (uint32_t)(as * 256 + h * 128);
+                    const uint32_t a_hi = base + EvalSmem::A + h * (EV_A_BYTES / 2), a_lo = a_hi + EV_A_BYTES;
+                    const uint32_t b_hi = base + EvalSmem::B + s * 2 * EV_B_BYTES, b_lo = b_hi + EV_B_BYTES;
+                    // small terms first: hi.lo, lo.hi, then hi.hi
 #pragma unroll
-                    for (int k = 0; k < EV_D / 16; ++k) {
-                        const uint64_t da = umma_desc(base + EvalSmem::A + h * (EV_A_BYTES / 2) + k * 256);
-                        const uint64_t db = umma_desc(base + EvalSmem::B + s * EV_B_BYTES + k * 256);
-                        tc_mma_bf16(d, da, db, EV_IDESC, k > 0 ? 1u : 0u);
+                    for (int t = 0; t < 3; ++t) {
+                        const uint32_t a_t = t == 1 ? a_lo : a_hi;
+                        const uint32_t b_t = t == 0 ? b_lo : b_hi;
+#pragma unroll
+                        for (int k = 0; k < EV_D / 16; ++k)
+                            tc_mma_bf16(d, umma_desc(a_t + k * 256), umma_desc(b_t + k * 256), EV_IDESC, (t | k) ? 1u : 0u);
                     }
                 }
                 tc_commit(bar_empty + 8 * s);    // smem slot reusable once these MMAs have read it
@@ -577,6 +593,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
         keep_key = (unsigned long long)orderable(tau_a - slack[row]) << 32;
     }
     int n_keep = 0;
+    float worst = 0.f;  // largest |approximate - exact| among the re-scored candidates
     for (int j0 = 0; j0 < n_c; j0 += 32) {
         const int j = j0 + lane;
         bool ok = false;
@@ -586,7 +603,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
             ok = k >= keep_key;
             if (ok) {
                 const int id = (int32_t)(0xffffffffu - (uint32_t)(k & 0xffffffffu));
-                nk = rank_key(exact_score(u_sm[warp], item_emb + (int64_t)id * D, D), id);
+                const float ex = exact_score(u_sm[warp], item_emb + (int64_t)id * D, D);
+                const uint32_t ob = (uint32_t)(k >> 32);
+                worst = fmaxf(worst, fabsf(__uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob) - ex));
+                nk = rank_key(ex, id);
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -595,9 +615,13 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
         n_keep += __popc(m);
         __syncwarp();
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
     if (lane == 0 && stats) {
         atomicAdd(stats + 0, (unsigned long long)n_c);
         atomicAdd(stats + 1, (unsigned long long)n_keep);
+        // observed error in parts per million of the bound eps = slack / 2 (must stay below 1e6)
+        atomicMax(stats + 3, (unsigned long long)(worst / (0.5f * slack[row]) * 1.0e6f));
     }
     // (d) K rounds: best exact key strictly below the previous winner
     prev = ~0ull;
@@ -788,8 +812,8 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
     if (p.n_brute_blocks > n_test && n_test > 0) p.n_brute_blocks = (int)n_test;
     size_t o = 0;
     if (p.tensor) {
-        p.off_ap = o; o = align_up(o + (size_t)p.n_test_pad * EV_D * 2, 256);
-        p.off_bp = o; o = align_up(o + (size_t)p.n_items_pad * EV_D * 2, 256);
+        p.off_ap = o; o = align_up(o + (size_t)p.n_test_pad * EV_D * 2 * 2, 256);
+        p.off_bp = o; o = align_up(o + (size_t)p.n_items_pad * EV_D * 2 * 2, 256);
         p.off_slack = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
         p.off_maxnorm = o; o = align_up(o + 256, 256);
         p.off_bucket = o; o = align_up(o + (size_t)p.n_seg * p.n_test_pad * EV_BUCKETS * 4, 256);
@@ -860,6 +884,8 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
         memset(&P, 0, sizeof(P));
         P.Ap = Ap;
         P.Bp = Bp;
+        P.a_term_stride = p.n_test_pad * EV_D * 2;
+        P.b_term_stride = p.n_items_pad * EV_D * 2;
         P.test_users = test_users;
         P.train_indptr = train_indptr;
         P.train_indices = train_indices;

@@ -1,0 +1,314 @@
+"""Row-partitioned propagation across the GPUs of one NVSwitch box.
+
+The reference is single-process; this module is the scaling axis the north star adds:
+
+* **Partition.**  Users and items are each cut into ``world`` contiguous ranges; rank ``r`` owns user range
+  ``r`` and item range ``r``: their CSR rows, embedding rows and optimiser state.  Owned rows are laid out
+  ``[own users | own items | padding]`` (``n_loc`` rows, equal on every rank), so the gathered table is the
+  concatenation of the ranks' blocks: node ``v`` sits at ``perm(v) = owner(v) * n_loc + offset(v)``.
+* **Local matrix.**  ``A_loc = A[own rows, :]`` with columns renumbered by ``perm`` but kept in their
+  ORIGINAL ascending order inside a row, so each output row is accumulated in exactly the order of the
+  single-GPU kernel: the sharded result is bit-identical to the unsharded one.
+* **Exchange.**  One ``all_gather`` of the owned rows per propagation (NCCL over NVLink 5 / NVSwitch), then the
+  same ``hgr_spmm_f32`` kernel on ``A_loc``.  The normalised adjacency is symmetric, so the backward pass is
+  ``dX_own = A_loc . all_gather(dY_own)``: a gather, never a reduction.
+* **Loss.**  The final tables are gathered once; every rank evaluates the fused BPR + L2 kernel on the whole
+  batch (identical numbers on all ranks), so the gradient of the gather is a slice.  Gradients of the small
+  replicated parameters (LayerNorm, Linear) are summed with one ``all_reduce``.
+* **Evaluation** shards the test users: each rank ranks its own users against the gathered item table.
+
+The kernel set is a constructor argument so the host logic (partition maps, gathers, autograd wiring) is
+exercised by the world_size-2 ``gloo`` CPU tests with an injected CPU matrix product; the product default is
+libhgr.so and nothing else.
+"""
+from __future__ import annotations
+
+import types
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class Partition:
+    """Ownership maps of the 1-D row partition."""
+    n_users: int
+    n_items: int
+    world: int
+
+    def __post_init__(self):
+        self.up = -(-self.n_users // self.world)  # users per rank (last rank may own fewer)
+        self.ip = -(-self.n_items // self.world)
+        self.n_loc = -(-(self.up + self.ip) // 4) * 4  # rows per rank, padded
+        self.n_glob = self.n_loc * self.world
+
+    def users_of(self, rank):
+        return min(rank * self.up, self.n_users), min((rank + 1) * self.up, self.n_users)
+
+    def items_of(self, rank):
+        return min(rank * self.ip, self.n_items), min((rank + 1) * self.ip, self.n_items)
+
+    def perm_user(self, u: torch.Tensor) -> torch.Tensor:
+        u = u.to(torch.int64)
+        return torch.div(u, self.up, rounding_mode="floor") * self.n_loc + u % self.up
+
+    def perm_item(self, i: torch.Tensor) -> torch.Tensor:
+        i = i.to(torch.int64)
+        return torch.div(i, self.ip, rounding_mode="floor") * self.n_loc + self.up + i % self.ip
+
+
+def local_block(part: Partition, rank: int, u: torch.Tensor, i: torch.Tensor):
+    """``A[own rows, :]`` of the normalised bipartite adjacency of the UNIQUE pairs ``(u, i)``, as
+    ``(indptr int64 [n_loc + 1], indices int32, values float32)`` with permuted column ids stored in original
+    ascending-id order.  Values are ``d[row] * d[col]`` with ``d = np.power(deg, -0.5)`` (one fp32 multiply, the value
+    scipy's ``D A D`` product leaves for unit weights): bit-identical to ``Interaction.norm_adj``."""
+    dev = u.device
+    u = u.to(torch.int64)
+    i = i.to(torch.int64)
+    deg_u = torch.bincount(u, minlength=part.n_users)
+    deg_i = torch.bincount(i, minlength=part.n_items)
+    # deg^-1/2 through the host's np.power table, like graph.build_norm_adj: numpy's float32 pow is what the
+    # reference's values are made of and it is not correctly rounded
+    from .graph import host_pow_lut
+
+    max_deg = int(max(deg_u.max().item() if deg_u.numel() else 0, deg_i.max().item() if deg_i.numel() else 0))
+    lut = torch.from_numpy(host_pow_lut(max_deg + 1, -0.5)).to(dev)
+    du, di = lut[deg_u], lut[deg_i]
+    u0, u1 = part.users_of(rank)
+    i0, i1 = part.items_of(rank)
+    # user rows: columns are items, ascending item id
+    m = (u >= u0) & (u < u1)
+    key = torch.sort((u[m] - u0) * part.n_items + i[m]).values
+    ru, ci = torch.div(key, part.n_items, rounding_mode="floor"), key % part.n_items
+    # item rows: columns are users, ascending user id
+    m = (i >= i0) & (i < i1)
+    key = torch.sort((i[m] - i0) * part.n_users + u[m]).values
+    ri, cu = torch.div(key, part.n_users, rounding_mode="floor"), key % part.n_users
+    del key, m
+    counts = torch.zeros(part.n_loc, dtype=torch.int64, device=dev)
+    counts[:u1 - u0] = deg_u[u0:u1]
+    counts[part.up:part.up + (i1 - i0)] = deg_i[i0:i1]
+    indptr = torch.zeros(part.n_loc + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    indices = torch.cat([part.perm_item(ci), part.perm_user(cu)]).to(torch.int32)
+    values = torch.cat([du[ru + u0] * di[ci], di[ri + i0] * du[cu]])
+    return indptr, indices, values
+
+
+class LibhgrKernels:
+    """The product kernels (libhgr.so).  The gloo CPU tests pass an object with the same three methods built on
+    a CPU matrix product to exercise the partition / gather / autograd logic without a GPU."""
+
+    @staticmethod
+    def make_block(indptr, indices, values, shape):
+        from .graph import DeviceCSR
+
+        return DeviceCSR(indptr, indices, values, shape)  # rows are long-tailed like the global matrix: split plan kept
+
+    @staticmethod
+    def spmm(block, x, ep=None):
+        """``epilogue(block @ x)``; ``ep`` is a dict of ``ops.make_epilogue`` keyword arguments."""
+        from . import ops
+
+        return ops.spmm_raw(block, x, ops.make_epilogue(**ep) if ep else None)
+
+    @staticmethod
+    def leaky_ln_bwd(pre, dy, gamma, eps, slope):
+        from . import ops
+
+        return ops.leaky_ln_bwd(pre, dy, gamma, eps, slope)
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """``[n_loc, D]`` owned rows -> ``[world * n_loc, D]``.  ``grad_mode``: ``'slice'`` when every rank holds the
+    same full gradient (replicated loss), ``'reduce'`` for a reduce-scatter of per-rank partial gradients."""
+
+    @staticmethod
+    def forward(ctx, x, g, grad_mode):
+        ctx.g, ctx.grad_mode = g, grad_mode
+        return g.all_gather(x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = ctx.g
+        if ctx.grad_mode == "slice":
+            return grad[g.rank * g.part.n_loc:(g.rank + 1) * g.part.n_loc].contiguous(), None, None
+        out = torch.empty((g.part.n_loc, grad.shape[1]), dtype=grad.dtype, device=grad.device)
+        dist.reduce_scatter_tensor(out, grad.contiguous(), group=g.group)
+        return out, None, None
+
+
+class _DistSpmm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g):
+        ctx.g = g
+        return g.k.spmm(g.block, g.all_gather(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.g  # A symmetric: dX_own = (A^T dY)[own] = A[own, :] dY
+        return g.k.spmm(g.block, g.all_gather(dy.contiguous())), None
+
+
+class DistGraph:
+    """The rank's block of the adjacency + the communicator.  Quacks like the ``DeviceCSR`` the encoders hold
+    (``shape``, ``_nnz``, ``t``) and routes ``ops.spmm / hgconv / lightgcn_propagate`` to the sharded forms."""
+
+    def __init__(self, part: Partition, rank: int, indptr, indices, values, group=None, kernels=None):
+        self.part, self.rank, self.world, self.group = part, rank, part.world, group
+        self.k = kernels or LibhgrKernels
+        self.block = self.k.make_block(indptr, indices, values, (part.n_loc, part.n_glob))
+        self.shape = (part.n_glob, part.n_glob)
+        self.symmetric = True
+        self.device = indptr.device
+        self._nnz_local = int(indices.numel())
+        self.gather_events = None  # bench: list of (start, end) CUDA events around every all_gather
+
+    def _nnz(self):
+        return self._nnz_local
+
+    def t(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    cuda = to
+
+    def all_gather(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.contiguous()
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        if self.gather_events is not None and x.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather_into_tensor(out, x, group=self.group)
+            e1.record()
+            self.gather_events.append((e0, e1))
+        else:
+            dist.all_gather_into_tensor(out, x, group=self.group)
+        return out
+
+    # ---- sharded operators (same signatures as ops.*) ------------------------------------------
+    def spmm(self, x):
+        return _DistSpmm.apply(x, self)
+
+    def lightgcn_propagate(self, ego, n_layers, sum_readout=False):
+        """``mean_k A^k E`` on owned rows: one gather + one local propagation per layer; the last layer's
+        readout (sum of the layer tables, scale) is fused into its kernel epilogue as in the local form."""
+        return _DistLightGCN.apply(ego, self, n_layers, sum_readout)
+
+    def hgconv(self, x, slope=None, ln_weight=None, ln_bias=None, residual=None, eps=1e-5):
+        return _DistHGConv.apply(x, ln_weight, ln_bias, residual, self, slope, eps)
+
+    def gather_tables(self, own: torch.Tensor, grad_mode="slice") -> torch.Tensor:
+        return _AllGatherRows.apply(own, self, grad_mode)
+
+
+def _lightgcn_rows(g: DistGraph, e0, n_layers, sum_readout):
+    if n_layers == 0:
+        return e0.clone()
+    layers = [e0]
+    cur = e0
+    for k in range(n_layers):
+        full = g.all_gather(cur)
+        if k + 1 < n_layers:
+            cur = g.k.spmm(g.block, full)
+            layers.append(cur)
+        else:
+            cur = g.k.spmm(g.block, full, dict(addends=layers, scale=1.0 if sum_readout else 1.0 / (n_layers + 1)))
+    return cur
+
+
+class _DistLightGCN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e0, g, n_layers, sum_readout):
+        ctx.g, ctx.n_layers, ctx.sum_readout = g, n_layers, sum_readout
+        return _lightgcn_rows(g, e0.contiguous(), n_layers, sum_readout)
+
+    @staticmethod
+    def backward(ctx, dout):
+        # out = c sum_k A^k e0 and A symmetric: the same sharded recurrence applied to dout
+        return _lightgcn_rows(ctx.g, dout.contiguous(), ctx.n_layers, ctx.sum_readout), None, None, None
+
+
+class _DistHGConv(torch.autograd.Function):
+    """Sharded ``[LN](leaky(A (A x))) [+ residual]``: two gathers + two local propagations; activation,
+    LayerNorm and residual stay fused in the second kernel's epilogue (they are row-local)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, g, slope, eps):
+        need_pre = (slope is not None or gamma is not None) and any(ctx.needs_input_grad[:3])
+        t = g.k.spmm(g.block, g.all_gather(x.contiguous()))
+        pre = torch.empty_like(t) if need_pre else None
+        gm = gamma.contiguous() if gamma is not None else None
+        bt = beta.contiguous() if beta is not None else None
+        rs = residual.contiguous() if residual is not None else None
+        y = g.k.spmm(g.block, g.all_gather(t), dict(slope=slope, gamma=gm, beta=bt, eps=eps, residual=rs, pre=pre))
+        ctx.g, ctx.slope, ctx.eps = g, slope, eps
+        ctx.has_ln, ctx.has_res = gamma is not None, residual is not None
+        ctx.save_for_backward(pre, gm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        pre, gamma = ctx.saved_tensors
+        g = ctx.g
+        dy = dy.contiguous()
+        dgamma = dbeta = None
+        if pre is not None:
+            dz, dgamma, dbeta = g.k.leaky_ln_bwd(pre, dy, gamma if ctx.has_ln else None, ctx.eps, ctx.slope)
+        else:
+            dz = dy
+        dx = None
+        if ctx.needs_input_grad[0]:
+            t = g.k.spmm(g.block, g.all_gather(dz))
+            dx = g.k.spmm(g.block, g.all_gather(t))
+        return dx, dgamma, dbeta, (dy if ctx.has_res else None), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# construction + training step
+# ------------------------------------------------------------------------------------------------
+def build_partitioned(u, i, n_users, n_items, rank, world, device=None, group=None, kernels=None):
+    """Every rank holds the same interaction list (synthetic generator, same seed) and keeps its own rows.
+    Returns a namespace with ``adj`` (DistGraph), ``data`` (what the encoders read: local ``n_users`` /
+    ``n_items`` and the adjacency handle) and ``part``."""
+    part = Partition(n_users, n_items, world)
+    indptr, indices, values = local_block(part, rank, u, i)
+    adj = DistGraph(part, rank, indptr, indices, values, group=group, kernels=kernels)
+    data = types.SimpleNamespace(n_users=part.up, n_items=part.n_loc - part.up, norm_adj=None, norm_adj_device=adj)
+    return types.SimpleNamespace(adj=adj, data=data, part=part)
+
+
+def sync_replicated_grads(model, owned_names=("embedding_dict.user_emb", "embedding_dict.item_emb"), group=None):
+    """Sum the gradients of the parameters every rank holds a copy of (LayerNorm, Linear); the embedding rows
+    are owned, not replicated.  One flat all_reduce."""
+    grads = [p.grad for n, p in model.named_parameters() if p.grad is not None and not n.endswith(owned_names)]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def train_step(model, optimizer, g: DistGraph, user_idx, pos_idx, neg_idx, reg: float, batch_size: int, loss_fn=None):
+    """One sharded step of the reference's training loop (model/graph/LightGCN.py:49-66): propagate the owned
+    rows, gather the final tables, fused BPR + L2 on the whole batch, backward, summed replicated gradients,
+    optimiser step on the owned rows.  ``user_idx / pos_idx / neg_idx`` are GLOBAL dense ids."""
+    if loss_fn is None:
+        from .loss_torch import bpr_l2_from_tables as loss_fn
+    out_u, out_i = model()[:2]
+    full = g.gather_tables(torch.cat([out_u, out_i], 0))
+    part = g.part
+    rec_loss, reg_loss = loss_fn(full, full, part.perm_user(user_idx), part.perm_item(pos_idx), part.perm_item(neg_idx), reg,
+                                 batch_size)
+    optimizer.zero_grad(set_to_none=True)
+    (rec_loss + reg_loss).backward()
+    if g.world > 1:
+        sync_replicated_grads(model, group=g.group)
+    optimizer.step()
+    return torch.stack([rec_loss.detach(), reg_loss.detach()])

@@ -70,6 +70,29 @@ def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addend
     return ep
 
 
+make_epilogue = _epilogue
+
+
+def leaky_ln_bwd(pre, dy, gamma, eps, slope):
+    """Backward of ``LayerNorm(leaky_relu(pre)) * gamma + beta`` (hgr_leaky_ln_bwd_f32): returns
+    ``(dpre, dgamma, dbeta)``; ``gamma is None`` means no LayerNorm."""
+    d = dy.shape[1]
+    dz = torch.empty_like(dy)
+    dgamma = dbeta = parts = None
+    if gamma is not None:
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        parts = torch.empty((_lib.lib().hgr_ln_bwd_partial_rows(dy.shape[0]), 2, d), dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.lib().hgr_leaky_ln_bwd_f32(pre.data_ptr(), dy.data_ptr(), _lib.ptr(gamma), float(eps), 0 if slope is None else 1,
+                                               0.0 if slope is None else float(slope), dy.shape[0], d, dz.data_ptr(), _lib.ptr(dgamma),
+                                               _lib.ptr(dbeta), _lib.ptr(parts), _lib.stream_ptr()))
+    return dz, dgamma, dbeta
+
+
+def _sharded(adj) -> bool:
+    """A ``dist.DistGraph`` (rows partitioned across ranks) instead of a whole-matrix ``DeviceCSR``."""
+    return getattr(adj, "world", 0) >= 1 and hasattr(adj, "part")
+
+
 def _ws(a: DeviceCSR, d: int):
     ws = a.workspace(d)
     return (None, 0) if ws is None else (ws.data_ptr(), ws.numel() * 4)
@@ -115,6 +138,8 @@ class _Spmm(torch.autograd.Function):
 
 def spmm(adj: DeviceCSR, x: torch.Tensor) -> torch.Tensor:
     """Drop-in for ``torch.sparse.mm(adj, x)``; backward is ``adj.t() @ dy`` through the same kernel."""
+    if _sharded(adj):
+        return adj.spmm(x)
     return _Spmm.apply(x, adj)
 
 
@@ -138,17 +163,7 @@ class _HGConv(torch.autograd.Function):
         dy = dy.contiguous()
         dgamma = dbeta = None
         if pre is not None:
-            d = dy.shape[1]
-            dz = torch.empty_like(dy)
-            if ctx.has_ln:
-                dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
-                parts = torch.empty((_lib.lib().hgr_ln_bwd_partial_rows(dy.shape[0]), 2, d), dtype=torch.float32, device=dy.device)
-            else:
-                parts = None
-            _lib.check(_lib.lib().hgr_leaky_ln_bwd_f32(pre.data_ptr(), dy.data_ptr(), _lib.ptr(gamma), float(ctx.eps),
-                                                       0 if ctx.slope is None else 1, 0.0 if ctx.slope is None else float(ctx.slope),
-                                                       dy.shape[0], d, dz.data_ptr(), _lib.ptr(dgamma), _lib.ptr(dbeta),
-                                                       _lib.ptr(parts), _lib.stream_ptr()))
+            dz, dgamma, dbeta = leaky_ln_bwd(pre, dy, gamma if ctx.has_ln else None, ctx.eps, ctx.slope)
         else:
             dz = dy
         # y = f(A (At x))  =>  dx = At^T (A^T dz) = A (At dz) evaluated with the roles swapped
@@ -170,6 +185,8 @@ def hgconv(adj: DeviceCSR, x: torch.Tensor, slope: float | None = None, ln_weigh
     wraps every HGCNConv call in the reference; ``residual`` fuses the ``+ res``."""
     if (ln_weight is None) != (ln_bias is None):
         raise ValueError("ln_weight and ln_bias must be given together")
+    if _sharded(adj):
+        return adj.hgconv(x, slope, ln_weight, ln_bias, residual, eps)
     return _HGConv.apply(x, ln_weight, ln_bias, residual, adj, slope, eps)
 
 
@@ -203,4 +220,6 @@ def lightgcn_propagate(adj: DeviceCSR, ego: torch.Tensor, n_layers: int, sum_rea
     """``mean_k (adj^k @ ego)`` for k = 0..n_layers (``sum_readout``: the plain sum) -- the body of
     ``LGCN_Encoder.forward`` in ``n_layers`` launches; E^L and the stacked [N, L+1, D] tensor of the
     reference are never materialised."""
+    if _sharded(adj):
+        return adj.lightgcn_propagate(ego, n_layers, sum_readout)
     return _LightGCN.apply(ego, adj, n_layers, sum_readout)

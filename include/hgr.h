@@ -197,11 +197,13 @@ int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
  * mode 0 ("exact"):    true top-K, score descending, ties by ascending item id, no duplicates.
  * mode 1 ("refquirk"): find_k_largest as shipped, which visits the first K candidates twice, so an item
  *                      with id < K that makes the list appears twice; K <= 64.
- * engine 0: tcgen05 tensor path when D == 64 and K <= 64 (bf16 candidate generation with a proven error
- *           bound, exact fp32 re-scoring of the candidates; results identical to engine 1), else SIMT.
+ * engine 0: tcgen05 tensor path when D == 64 and K <= 64 (candidate generation with 2 x bf16 split operands
+ *           and a proven error bound, exact fp32 re-scoring of the candidates; results identical to
+ *           engine 1), else SIMT.
  * engine 1: SIMT fp32 brute force.   engine 2: tensor path or HGR_ERR_INVALID.
  * stats (device uint64[4], optional, caller zeroes): candidates emitted by the tensor stage, candidates
- * re-scored, users that overflowed to the brute-force fallback, reserved.
+ * re-scored, users that overflowed to the brute-force fallback, and the largest observed
+ * |tensor score - fp32 score| in parts per million of the proven error bound (always < 1e6).
  * ------------------------------------------------------------------------------------------- */
 size_t hgr_fullrank_topk_workspace_bytes(int64_t n_test, int64_t n_items, int32_t D, int32_t K, int32_t engine);
 int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *item_emb, int64_t n_items, int32_t D,
