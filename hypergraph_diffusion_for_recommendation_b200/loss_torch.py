@@ -1,5 +1,7 @@
 """Losses of the reference's ``util/loss_torch.py`` on libhgr.so.
 
+``contrastLoss`` / ``InfoNCE`` (util/loss_torch.py:103-110, 32-40) run on csrc/loss_ssl.cu.
+
 ``bpr_l2_from_tables`` is the fused product path: gathers + BPR + L2 in one forward launch and one
 backward launch (reference: ``rec_user_emb[user_idx]`` ... ``bpr_loss`` ... ``l2_reg_loss / batch_size``,
 model/graph/LightGCN.py:52-55).  ``bpr_loss`` / ``l2_reg_loss`` keep the reference signatures
@@ -74,3 +76,59 @@ def l2_reg_loss(reg, *args):
     for emb in args:
         emb_loss = emb_loss + torch.norm(emb, p=2)
     return emb_loss * reg
+
+
+class _SslLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e1, e2, nodes, temp, kind, normalize):
+        if not (e1.is_cuda and e2.is_cuda):
+            raise _lib.HgrError("embedding tables must be CUDA tensors (no CPU path)")
+        if e1.dtype != torch.float32 or e2.dtype != torch.float32 or e1.dim() != 2 or e2.dim() != 2 or e1.shape[1] != e2.shape[1]:
+            raise TypeError("operands must be 2-D float32 with equal width")
+        e1, e2 = e1.contiguous(), e2.contiguous()
+        dev = e1.device
+        if nodes is not None:
+            nodes = _idx(nodes, dev)
+            m = int(nodes.numel())
+        else:
+            if e1.shape[0] != e2.shape[0]:
+                raise ValueError("views differ in length")
+            m = int(e1.shape[0])
+        d = int(e1.shape[1])
+        lib = _lib.lib()
+        nbytes = int(lib.hgr_ssl_workspace_bytes(m, d))
+        saved = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-saved.data_ptr()) % 256
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.hgr_ssl_loss_fwd_f32(e1.data_ptr(), e2.data_ptr(), e1.shape[0], e2.shape[0], d, _lib.ptr(nodes), m, float(temp),
+                                            int(kind), int(normalize), loss.data_ptr(), saved.data_ptr() + off, nbytes, bad.data_ptr(),
+                                            _lib.stream_ptr()))
+        ctx.save_for_backward(saved, nodes if nodes is not None else torch.empty(0, device=dev))
+        ctx.meta = (e1.shape, e2.shape, d, m, float(temp), int(normalize), off, nbytes, nodes is not None)
+        ctx.bad = bad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        saved, nodes = ctx.saved_tensors
+        s1, s2, d, m, temp, normalize, off, nbytes, has_nodes = ctx.meta
+        dev = saved.device
+        d1 = torch.zeros(s1, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        d2 = torch.zeros(s2, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        g = grad.reshape(1).contiguous().to(torch.float32)
+        _lib.check(_lib.lib().hgr_ssl_loss_bwd_f32(s1[0], s2[0], d, nodes.data_ptr() if has_nodes else None, m, temp, normalize,
+                                                   saved.data_ptr() + off, nbytes, g.data_ptr(), _lib.ptr(d1), _lib.ptr(d2),
+                                                   _lib.stream_ptr()))
+        return d1, d2, None, None, None, None
+
+
+def contrastLoss(embeds1, embeds2, nodes, temp):
+    """util/loss_torch.py:103-110.  ``nodes`` must be unique (the reference passes ``torch.unique``); only the picked
+    rows are normalised and the [M, M] logits stay on chip."""
+    return _SslLoss.apply(embeds1, embeds2, nodes, temp, 0, 1)
+
+
+def InfoNCE(view1, view2, temperature, b_cos=True):
+    """util/loss_torch.py:32-40."""
+    return _SslLoss.apply(view1, view2, None, temperature, 1, 1 if b_cos else 0)

@@ -212,6 +212,25 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
                           float *out_scores, uint64_t *stats, void *workspace, size_t workspace_bytes,
                           hgr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Contrastive (SSL) losses fused with their gathers and row normalisation (util/loss_torch.py).
+ *   kind 0  contrastLoss(embeds1, embeds2, nodes, temp)   util/loss_torch.py:103-110 (HCCF.py:62-66, HGNN_HD3.py:345-350)
+ *   kind 1  InfoNCE(view1, view2, temperature, b_cos)     util/loss_torch.py:32-40   (SGL.py:167-180)
+ * E1 [n_rows1, D], E2 [n_rows2, D]; nodes int64 [M] picks the rows (NULL: rows 0..M-1 of both tables, the InfoNCE
+ * call shape).  nodes must be unique (the reference passes torch.unique(...)).  normalize = F.normalize of the rows
+ * (always on for kind 0, b_cos for kind 1).  loss: device float[1].  `saved` (hgr_ssl_workspace_bytes(M, D), 256-byte
+ * aligned) carries the normalised rows, row sums and coefficients to the backward call.  The [M, M] logits are never
+ * materialised.  Backward: dE1 / dE2 ([n_rows, D], zero-filled by the caller; either may be NULL for a detached
+ * operand) receive grad_out[0] * d loss / d E at the picked rows.  Out-of-range nodes are counted in
+ * *bad_index_count (device int, caller zeroes) and contribute zero rows.
+ * ------------------------------------------------------------------------------------------- */
+size_t hgr_ssl_workspace_bytes(int64_t M, int32_t D);
+int hgr_ssl_loss_fwd_f32(const float *E1, const float *E2, int64_t n_rows1, int64_t n_rows2, int32_t D, const int64_t *nodes,
+                         int64_t M, float temp, int32_t kind, int32_t normalize, float *loss, void *saved, size_t saved_bytes,
+                         int32_t *bad_index_count, hgr_stream_t stream);
+int hgr_ssl_loss_bwd_f32(int64_t n_rows1, int64_t n_rows2, int32_t D, const int64_t *nodes, int64_t M, float temp, int32_t normalize,
+                         void *saved, size_t saved_bytes, const float *grad_out, float *dE1, float *dE2, hgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,3 +61,69 @@ def test_reference_signature_bpr_loss_and_bad_indices(L, golden):
     assert rel_err(L.l2_reg_loss(0.1, ue, pe, ne) / 2048, golden["loss_reg"]) < RTOL
     with pytest.raises(Exception):
         L.bpr_l2_from_tables(torch.from_numpy(ut), torch.from_numpy(it), torch.from_numpy(u), torch.from_numpy(p), torch.from_numpy(n), 0.1, 2048)
+
+
+# ------------------------------------------------------------------------------------ contrastLoss / InfoNCE (csrc/loss_ssl.cu)
+def test_contrast_loss_and_infonce_match_reference_golden(L, golden):
+    e1 = torch.from_numpy(golden["cl_e1"]).cuda().requires_grad_(True)
+    e2 = torch.from_numpy(golden["cl_e2"]).cuda().requires_grad_(True)
+    loss = L.contrastLoss(e1, e2, torch.from_numpy(golden["cl_nodes"]), float(golden["cl_temp"]))
+    assert rel_err(loss, golden["cl_loss"]) < RTOL
+    loss.backward()
+    assert rel_err(e1.grad, golden["cl_d1"]) < 5e-5 and rel_err(e2.grad, golden["cl_d2"]) < 5e-5
+    v1 = torch.from_numpy(golden["nce_v1"]).cuda().requires_grad_(True)
+    v2 = torch.from_numpy(golden["nce_v2"]).cuda().requires_grad_(True)
+    loss = L.InfoNCE(v1, v2, float(golden["nce_temp"]))
+    assert rel_err(loss, golden["nce_loss"]) < RTOL
+    loss.backward()
+    assert rel_err(v1.grad, golden["nce_d1"]) < 5e-5 and rel_err(v2.grad, golden["nce_d2"]) < 5e-5
+
+
+@pytest.mark.parametrize("d,n_rows,m", [(32, 40, 1), (64, 3000, 1111), (64, 5000, 4096), (128, 700, 65)])
+def test_contrast_loss_shapes_against_oracle_and_torch(L, d, n_rows, m):
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(m)
+    e1 = rng.standard_normal((n_rows, d)).astype(np.float32) * 0.3
+    e2 = rng.standard_normal((n_rows, d)).astype(np.float32) * 0.3
+    nodes = np.sort(rng.permutation(n_rows)[:m])
+    t1, t2 = torch.from_numpy(e1).cuda().requires_grad_(True), torch.from_numpy(e2).cuda().requires_grad_(True)
+    loss = L.contrastLoss(t1, t2, torch.from_numpy(nodes).cuda(), 0.2)
+    (3.0 * loss).backward()
+    o_loss, o_d1, o_d2 = O.contrast_loss(e1, e2, nodes, 0.2)
+    if m == 1:  # a single node: loss = log(1 + 1e-8 / e^x) ~ 0, gradients ~ 0 (pure cancellation)
+        assert abs(float(loss.detach()) - float(o_loss)) < 1e-6 and float(t1.grad.abs().max()) < 1e-6
+        return
+    assert rel_err(loss, o_loss) < RTOL
+    assert rel_err(t1.grad, 3.0 * o_d1) < 5e-5 and rel_err(t2.grad, 3.0 * o_d2) < 5e-5
+    # the reference's own expression in torch on the GPU (util/loss_torch.py:103-110), HCCF-style detached first view
+    r1, r2 = torch.from_numpy(e1).cuda(), torch.from_numpy(e2).cuda().requires_grad_(True)
+    a, b = F.normalize(r1 + 1e-8, p=2)[nodes], F.normalize(r2 + 1e-8, p=2)[nodes]
+    ref = -torch.log(torch.exp((a * b).sum(-1) / 0.2) / (torch.exp(a @ b.T / 0.2).sum(-1) + 1e-8)).mean()
+    ref.backward()
+    d2 = torch.from_numpy(e2).cuda().requires_grad_(True)
+    got = L.contrastLoss(torch.from_numpy(e1).cuda(), d2, torch.from_numpy(nodes), 0.2)  # CPU index tensor, detached e1
+    got.backward()
+    assert rel_err(got, ref) < RTOL and rel_err(d2.grad, r2.grad) < 5e-5
+
+
+@pytest.mark.parametrize("b_cos", [True, False])
+def test_infonce_against_torch_expression(L, b_cos):
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(17)
+    v1 = (rng.standard_normal((777, 64)) * (0.2 if not b_cos else 1.0)).astype(np.float32)
+    v2 = (v1 + 0.1 * rng.standard_normal((777, 64)) * (0.2 if not b_cos else 1.0)).astype(np.float32)
+    t1, t2 = torch.from_numpy(v1).cuda().requires_grad_(True), torch.from_numpy(v2).cuda().requires_grad_(True)
+    loss = L.InfoNCE(t1, t2, 0.2, b_cos)
+    loss.backward()
+    r1, r2 = torch.from_numpy(v1).cuda().requires_grad_(True), torch.from_numpy(v2).cuda().requires_grad_(True)
+    a, b = (F.normalize(r1, dim=1), F.normalize(r2, dim=1)) if b_cos else (r1, r2)
+    pos = torch.exp((a * b).sum(-1) / 0.2)
+    ttl = torch.exp(a @ b.T / 0.2).sum(1)
+    ref = (-torch.log(pos / ttl + 10e-6)).mean()
+    ref.backward()
+    assert rel_err(loss, ref) < RTOL and rel_err(t1.grad, r1.grad) < 5e-5 and rel_err(t2.grad, r2.grad) < 5e-5
+    if b_cos:
+        o_loss, o_d1, o_d2 = O.info_nce(v1, v2, 0.2)
+        assert rel_err(loss, o_loss) < RTOL and rel_err(t1.grad, o_d1) < 5e-5
