@@ -205,6 +205,48 @@ class EquivSetConv(nn.Module):
         return self.W(X)
 
 
+class EquivSetConvScatter(nn.Module):
+    """``EquivSetConv`` of the scatter form (model/layers/layers2/EquivSetConv2.py:37-100, = layers3/EquivSetConv3.py,
+    HCCF_diffusion.py:257-308): ``W1`` -> mean over each hyperedge -> ``W2`` -> mean over each vertex ->
+    restart mix -> ``W``.  The two ``torch_scatter.scatter(..., reduce='mean')`` calls become deterministic
+    propagations over a row-normalised incidence pair built once per (vertex, edges) index pair.  ``W2`` with
+    ``mlp2_layers == 0`` is the reference's slice (``Xev = Xe[E]``), the only form its configs use."""
+
+    def __init__(self, in_features, out_features, mlp1_layers=1, mlp2_layers=1, mlp3_layers=1, aggr='add', alpha=0.5,
+                 dropout=0., normalization='None', input_norm=False, hypergraph=None, data=None):
+        super().__init__()
+        if aggr != 'mean':
+            raise NotImplementedError("only reduce='mean' (the reference's configs) is on the B200 path")
+        if mlp2_layers > 0:
+            raise NotImplementedError("W2 as an MLP over [X[V], Xe[E]] pairs is not used by any shipped config")
+        self.W1 = MLP(in_features, out_features, out_features, mlp1_layers, dropout=dropout, Normalization=normalization,
+                      InputNorm=input_norm) if mlp1_layers > 0 else nn.Identity()
+        self.W = MLP(out_features, out_features, out_features, mlp3_layers, dropout=dropout, Normalization=normalization,
+                     InputNorm=input_norm) if mlp3_layers > 0 else nn.Identity()
+        self.aggr, self.alpha, self.dropout, self.data = aggr, alpha, dropout, data
+        self._inc_key, self._inc = None, None
+
+    def reset_parameters(self):
+        for m in (self.W1, self.W):
+            if isinstance(m, MLP):
+                m.reset_parameters()
+
+    def incidence(self, vertex, edges, n_nodes):
+        from .graph import build_incidence
+
+        key = (vertex.data_ptr(), edges.data_ptr(), int(vertex.numel()), int(n_nodes))
+        if key != self._inc_key:
+            self._inc, self._inc_key = build_incidence(vertex, edges, n_nodes, device=_device()), key
+        return self._inc
+
+    def forward(self, X, vertex, edges, X0):
+        inc = self.incidence(vertex, edges, X.shape[-2])
+        Xe = ops.segment_mean_to_edges(inc, self.W1(X))
+        Xv = ops.segment_mean_to_nodes(inc, Xe)
+        X = (1 - self.alpha) * Xv + self.alpha * X0
+        return self.W(X)
+
+
 class EquivSetGNN(nn.Module):
     def __init__(self, num_features, args, dense_hypergraph, data, ncount, mcount):
         super().__init__()

@@ -237,3 +237,37 @@ def build_interaction_csr(user_idx, item_idx, n_users: int, n_items: int, device
     out = DeviceCSR(indptr, indices, values, (nr, nc), chunk_nnz=chunk_nnz)
     out.degree = deg
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Hypergraph incidence for the scatter form of ED-HNN message passing
+# (model/layers/layers2/EquivSetConv2.py:85-100, EquivSetGNN2.py:105-133, HCCF_diffusion.py:291-308,382-402)
+# ------------------------------------------------------------------------------------------------
+class Incidence:
+    """Row-normalised incidence pair of a hypergraph given as (vertex, hyperedge) pairs:
+    ``to_edges = De^-1 H^T`` ([n_edges, n_nodes]) and ``to_nodes = Dv^-1 H`` ([n_nodes, n_edges]).
+    ``to_edges @ X`` is ``torch_scatter.scatter(X[V], E, reduce='mean')`` and ``to_nodes @ Xe`` is
+    ``scatter(Xe[E], V, reduce='mean', dim_size=n_nodes)``: an empty segment gives a zero row, exactly
+    pytorch-scatter's ``sum / clamp(count, 1)``.  Built once; the reference re-derives (V, E) with
+    ``torch.nonzero(H > 0)`` on a dense matrix every forward."""
+
+    def __init__(self, to_edges: DeviceCSR, to_nodes: DeviceCSR):
+        self.to_edges, self.to_nodes = to_edges, to_nodes
+        self.n_edges, self.n_nodes = to_edges.shape
+
+
+def build_incidence(vertex, edges, n_nodes: int, n_edges: int | None = None, device="cuda") -> Incidence:
+    dev = torch.device(device)
+    v, e = _as_i32(vertex, dev), _as_i32(edges, dev)
+    if n_edges is None:
+        n_edges = int(e.max().item()) + 1 if e.numel() else 0
+    # duplicated (v, e) pairs are summed into a multiplicity, like scatter() visiting the pair twice
+    to_nodes = build_interaction_csr(v, e, n_nodes, n_edges, device=dev, row_normalize=True)
+    to_edges = build_interaction_csr(v, e, n_nodes, n_edges, device=dev, transpose=True, row_normalize=True)
+    return Incidence(to_edges, to_nodes)
+
+
+def incidence_from_dense(h: torch.Tensor) -> Incidence:
+    """``generate_V_E`` (model/layers/layers2/EquivSetGNN2.py:105-133): pairs = ``nonzero(H > 0)``."""
+    nz = torch.nonzero(h > 0)
+    return build_incidence(nz[:, 0], nz[:, 1], h.shape[0], h.shape[1], device=h.device)

@@ -223,3 +223,20 @@ def lightgcn_propagate(adj: DeviceCSR, ego: torch.Tensor, n_layers: int, sum_rea
     if _sharded(adj):
         return adj.lightgcn_propagate(ego, n_layers, sum_readout)
     return _LightGCN.apply(ego, adj, n_layers, sum_readout)
+
+
+def scatter_mean_conv(inc, x: torch.Tensor) -> torch.Tensor:
+    """Scatter form of the node -> hyperedge -> node message passing (model/layers/layers2/EquivSetConv2.py:88-93
+    with identity MLPs): ``Xe = scatter_mean_E(X[V])``, ``Xv = scatter_mean_V(Xe[E])`` as two propagations over the
+    row-normalised incidence pair (``graph.Incidence``).  Deterministic (no atomics); differentiable."""
+    return spmm(inc.to_nodes, spmm(inc.to_edges, x))
+
+
+def segment_mean_to_edges(inc, x: torch.Tensor) -> torch.Tensor:
+    """``torch_scatter.scatter(X[V], E, dim=-2, reduce='mean')``"""
+    return spmm(inc.to_edges, x)
+
+
+def segment_mean_to_nodes(inc, xe: torch.Tensor) -> torch.Tensor:
+    """``torch_scatter.scatter(Xe[E], V, dim=-2, reduce='mean', dim_size=N)``"""
+    return spmm(inc.to_nodes, xe)

@@ -245,3 +245,54 @@ def test_hccf_encoder_matches_reference(hgr, golden, data):
     for l in range(2):
         assert rel_err(gcn_h[l], golden["hccf_gcn_%d" % l]) < RTOL
         assert rel_err(hyp_h[l], golden["hccf_hyp_%d" % l]) < 1e-4  # dense fp32 GEMM (cuBLAS may use a different order)
+
+
+# ------------------------------------------------------------------------------------ scatter-mean form
+def test_scatter_mean_form_matches_reference_golden_and_oracle(hgr, golden):
+    from hypergraph_diffusion_for_recommendation_b200 import graph
+
+    v, e, x = golden["scat_V"], golden["scat_E"], golden["scat_X"]
+    inc = graph.build_incidence(v, e, x.shape[0])
+    xt = cuda(x).requires_grad_(True)
+    y = hgr.ops.scatter_mean_conv(inc, xt)
+    assert rel_err(y, golden["scat_Y"]) < RTOL  # the reference's torch_scatter path
+    assert rel_err(y, O.scatter_mean_conv(v, e, x, x.shape[0])) < RTOL
+    # backward against torch autograd of the same index_add / clamp(count, 1) arithmetic
+    g = cuda(np.random.default_rng(2).standard_normal(x.shape).astype(np.float32))
+    (y * g).sum().backward()
+    import torch
+
+    xr = torch.from_numpy(x).requires_grad_(True)
+    vt, et = torch.from_numpy(v).long(), torch.from_numpy(e).long()
+    n_e = int(et.max()) + 1
+    xe = torch.zeros(n_e, x.shape[1]).index_add_(0, et, xr[vt]) / torch.bincount(et, minlength=n_e).clamp(min=1)[:, None]
+    xv = torch.zeros(x.shape[0], x.shape[1]).index_add_(0, vt, xe[et]) / torch.bincount(vt, minlength=x.shape[0]).clamp(min=1)[:, None]
+    (xv * g.cpu()).sum().backward()
+    assert rel_err(xt.grad, xr.grad) < RTOL
+
+
+def test_scatter_mean_ragged_incidence_with_empty_segments(hgr):
+    from hypergraph_diffusion_for_recommendation_b200 import encoders, graph
+
+    rng = np.random.default_rng(8)
+    n, n_e, d = 500, 64, 64
+    v = rng.integers(0, n - 50, 4000)          # the last 50 vertices belong to no hyperedge
+    e = rng.integers(0, n_e, 4000)
+    e[e == 13] = 12                            # hyperedge 13 is empty
+    pairs = np.unique(np.stack([v, e], 1), axis=0)
+    v, e = pairs[:, 0], pairs[:, 1]
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    inc = graph.build_incidence(v, e, n, n_e)
+    y = hgr.ops.scatter_mean_conv(inc, cuda(x))
+    assert rel_err(y, O.scatter_mean_conv(v, e, x, n)) < RTOL
+    assert float(y[-50:].abs().max()) == 0.0   # empty segments give zero rows
+    # the dense-incidence entry point of the reference (generate_V_E: nonzero(H > 0))
+    import torch
+
+    h = torch.zeros(n, n_e)
+    h[torch.from_numpy(v), torch.from_numpy(e)] = 0.7
+    inc2 = graph.incidence_from_dense(h.cuda())
+    assert rel_err(hgr.ops.scatter_mean_conv(inc2, cuda(x)), y) < 1e-6
+    conv = encoders.EquivSetConvScatter(d, d, mlp1_layers=0, mlp2_layers=0, mlp3_layers=0, aggr='mean', alpha=0.0)
+    out = conv(cuda(x), torch.from_numpy(v).cuda(), torch.from_numpy(e).cuda(), cuda(x))
+    assert rel_err(out, y) < 1e-6
