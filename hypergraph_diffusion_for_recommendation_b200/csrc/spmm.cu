@@ -9,9 +9,10 @@
 // (D = 64: a half warp reads one 256-byte row, a warp works on two output rows).  The group walks
 // its nonzeros in stored order and keeps ONE accumulator chain per feature, so a row that is not
 // split is accumulated with exactly the fused multiply-add sequence of the CPU oracle
-// (oracle/hgr_oracle.c) and is bit-identical to it.  Memory-level parallelism comes from issuing
-// the gathers of 8 consecutive nonzeros before the 8 dependent FMAs and from prefetching the next
-// (column, value) batch, not from splitting the sum.
+// (oracle/hgr_oracle.c) and is bit-identical to it.  Memory-level parallelism comes from keeping
+// the gathers of the next nonzeros in flight (cp.async into a shared-memory ring, default; or a
+// batch of register loads) while the current ones are accumulated, and from prefetching the next
+// (column, value) batches -- not from splitting the sum.
 //
 // Power-law rows.  Rows longer than plan.chunk_nnz are cut into chunks of chunk_nnz nonzeros; a
 // chunk is accumulated by one group into a partial row, and a second kernel adds the partials of a
@@ -27,7 +28,7 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 8;  // partial-row reduce kernel
 
 // Tuning variant (unroll depth of the gather batch x resident blocks per SM); see hgr_set_spmm_variant.
-static int g_variant = 0;  // 0 = gather batch 4, 6 blocks/SM
+static int g_variant = 0;  // 0 = cp.async ring of 2 x 4 rows per group, 6 blocks/SM
 
 template <int LPR, int UNR>
 __device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ idx, const float *__restrict__ val,
@@ -75,6 +76,91 @@ __device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ 
         c = cn;
         v = vn;
     }
+    return acc;
+}
+
+// cp.async variant of the gather: every lane copies ITS 16 bytes of the next RD embedding rows straight into a
+// per-thread ring in shared memory (LDGSTS, L1 bypass) and consumes them in order, so the number of row gathers in
+// flight is bounded by shared memory (RD x 256 B per row group) instead of by what the load/store unit tracks for
+// register loads.  The accumulation order is unchanged.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Lane gl of a row group holds (column, value) of nonzero `base + gl` of the current batch of LPR nonzeros and of the
+// next one (coalesced, prefetched); the embedding rows of sub-batch q + 1 (HB nonzeros) are in flight into one half of
+// the ring while sub-batch q is consumed from the other half.
+template <int LPR, int HB>
+__device__ __forceinline__ float4 gather_accumulate_async(const int32_t *__restrict__ idx, const float *__restrict__ val,
+                                                          const float4 *__restrict__ X4, int64_t s, int64_t e, int gl,
+                                                          unsigned gmask, float4 *__restrict__ ring /* stride kThreads */) {
+    static_assert(LPR % HB == 0, "sub-batch must divide the batch");
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s >= e) return acc;
+    int c = 0, cn = 0;
+    float v = 0.f, vn = 0.f;
+    if (s + gl < e) {
+        c = ld_stream_i32(idx + s + gl);
+        v = ld_stream_f32(val + s + gl);
+    }
+    if (s + LPR + gl < e) {
+        cn = ld_stream_i32(idx + s + LPR + gl);
+        vn = ld_stream_f32(val + s + LPR + gl);
+    }
+    // sub-batch 0 of the first batch
+#pragma unroll
+    for (int k = 0; k < HB; ++k) {
+        const int cc = __shfl_sync(gmask, c, k, LPR);
+        if (s + k < e) cp_async16(ring + k * kThreads, X4 + (int64_t)cc * LPR + gl);
+    }
+    cp_async_commit();
+    int half = 0;
+    for (int64_t base = s; base < e; base += LPR) {
+        // (column, value) of the batch after next
+        int c2 = 0;
+        float v2 = 0.f;
+        if (base + 2 * LPR + gl < e) {
+            c2 = ld_stream_i32(idx + base + 2 * LPR + gl);
+            v2 = ld_stream_f32(val + base + 2 * LPR + gl);
+        }
+#pragma unroll
+        for (int q = 0; q < LPR / HB; ++q) {
+            const int64_t sub = base + q * HB;  // first nonzero of the sub-batch being consumed
+            if (sub >= e) break;
+            // issue the next sub-batch (q + 1 of this batch, or 0 of the next batch) into the other half
+            const int64_t nsub = sub + HB;
+#pragma unroll
+            for (int k = 0; k < HB; ++k) {
+                const int src = (q + 1 < LPR / HB) ? (q + 1) * HB + k : k;
+                const int cc = __shfl_sync(gmask, (q + 1 < LPR / HB) ? c : cn, src, LPR);
+                if (nsub + k < e) cp_async16(ring + ((half ^ 1) * HB + k) * kThreads, X4 + (int64_t)cc * LPR + gl);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();  // everything but the group just committed has landed: sub-batch q is in `half`
+#pragma unroll
+            for (int k = 0; k < HB; ++k) {
+                const float vv = __shfl_sync(gmask, v, q * HB + k, LPR);
+                if (sub + k < e) {
+                    const float4 x = ring[(half * HB + k) * kThreads];
+                    acc.x = fmaf(vv, x.x, acc.x);
+                    acc.y = fmaf(vv, x.y, acc.y);
+                    acc.z = fmaf(vv, x.z, acc.z);
+                    acc.w = fmaf(vv, x.w, acc.w);
+                }
+            }
+            half ^= 1;
+        }
+        c = cn;
+        v = vn;
+        cn = c2;
+        vn = v2;
+    }
+    cp_async_wait<0>();
     return acc;
 }
 
@@ -166,6 +252,35 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_kernel(hgr_csr_t A, 
     finish_row<LPR>(acc, row, gl, gmask, ep, Y);
 }
 
+template <int LPR, int HB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) spmm_rows_async_kernel(hgr_csr_t A, const float4 *__restrict__ X4,
+                                                                   float *__restrict__ Y, hgr_epilogue_t ep,
+                                                                   float4 *__restrict__ partials, int heavy_blocks) {
+    extern __shared__ float4 spmm_ring[];  // [2 * HB][kThreads]
+    constexpr int GPB = kThreads / LPR;
+    const int gl = threadIdx.x % LPR;
+    const int g = threadIdx.x / LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
+    float4 *ring = spmm_ring + threadIdx.x;
+    if ((int)blockIdx.x < heavy_blocks) {
+        const int64_t chunk = (int64_t)blockIdx.x * GPB + g;
+        if (chunk >= A.n_chunks) return;
+        const int h = A.chunk_owner[chunk];
+        const int row = A.heavy_rows[h];
+        const int64_t s = A.indptr[row] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
+        const int64_t row_end = A.indptr[row + 1];
+        const int64_t e = s + A.chunk_nnz < row_end ? s + A.chunk_nnz : row_end;
+        partials[chunk * LPR + gl] = gather_accumulate_async<LPR, HB>(A.indices, A.values, X4, s, e, gl, gmask, ring);
+        return;
+    }
+    const int64_t row = (int64_t)(blockIdx.x - heavy_blocks) * GPB + g;
+    if (row >= A.n_rows) return;
+    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
+    if (A.n_heavy_rows > 0 && e - s > (int64_t)A.chunk_nnz) return;
+    const float4 acc = gather_accumulate_async<LPR, HB>(A.indices, A.values, X4, s, e, gl, gmask, ring);
+    finish_row<LPR>(acc, row, gl, gmask, ep, Y);
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A, const float4 *__restrict__ partials,
                                                                      float *__restrict__ Y, hgr_epilogue_t ep) {
@@ -235,16 +350,41 @@ static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_e
     return HGR_OK;
 }
 
+template <int LPR, int HB, int MINB>
+static int launch_spmm_async(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws, cudaStream_t st) {
+    constexpr int GPB = kThreads / LPR;
+    float4 *partials = reinterpret_cast<float4 *>(ws);
+    const int64_t heavy_blocks = A.n_heavy_rows > 0 ? ceil_div(A.n_chunks, GPB) : 0;
+    const int64_t grid = heavy_blocks + ceil_div(A.n_rows, GPB);
+    if (grid == 0) return HGR_OK;
+    HGR_REQUIRE(grid < (int64_t)0x7fffffff, "grid too large (%lld blocks)", (long long)grid);
+    const size_t smem = (size_t)2 * HB * kThreads * sizeof(float4);
+    HGR_CUDA_OK(cudaFuncSetAttribute(spmm_rows_async_kernel<LPR, HB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spmm_rows_async_kernel<LPR, HB, MINB><<<(unsigned)grid, kThreads, smem, st>>>(A, reinterpret_cast<const float4 *>(X), Y, ep,
+                                                                                 partials, (int)heavy_blocks);
+    HGR_LAUNCH_OK("spmm_rows_async_kernel");
+    if (A.n_heavy_rows > 0) {
+        spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, GPB), kThreads, 0, st>>>(A, partials, Y, ep);
+        HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
+    }
+    return HGR_OK;
+}
+
 template <int LPR>
 static int launch_spmm_variant(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws,
                                cudaStream_t st) {
-    // measured on B200 (profiles/spmm_variants_r1.md): resident warps beat deeper gather batches
+    // measured on B200 (profiles/spmm_variants_r1.md): resident warps beat deeper gather batches, and staging the
+    // gathered rows through shared memory with cp.async beats register loads by ~15 %
     switch (g_variant) {
         case 1: return launch_spmm<LPR, 8, 3>(A, X, Y, ep, ws, st);
         case 2: return launch_spmm<LPR, 8, 4>(A, X, Y, ep, ws, st);
         case 3: return launch_spmm<LPR, 4, 5>(A, X, Y, ep, ws, st);
         case 4: return launch_spmm<LPR, 2, 8>(A, X, Y, ep, ws, st);
-        default: return launch_spmm<LPR, 4, 6>(A, X, Y, ep, ws, st);
+        case 5: return launch_spmm<LPR, 4, 6>(A, X, Y, ep, ws, st);
+        case 6: return launch_spmm_async<LPR, 8, 3>(A, X, Y, ep, ws, st);
+        case 7: return launch_spmm_async<LPR, 2, 8>(A, X, Y, ep, ws, st);
+        case 8: return launch_spmm_async<LPR, 4, 7>(A, X, Y, ep, ws, st);
+        default: return launch_spmm_async<LPR, 4, 6>(A, X, Y, ep, ws, st);
     }
 }
 
@@ -279,7 +419,7 @@ static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, co
 extern "C" {
 
 int hgr_set_spmm_variant(int variant) {
-    HGR_REQUIRE(variant >= 0 && variant <= 4, "variant %d out of range", variant);
+    HGR_REQUIRE(variant >= 0 && variant <= 8, "variant %d out of range", variant);
     hgr::g_variant = variant;
     return HGR_OK;
 }

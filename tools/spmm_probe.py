@@ -20,7 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="52000x92000x3000000,1250000x250000x125000000")
     ap.add_argument("--chunks", default="0")
-    ap.add_argument("--variants", default="0")
+    ap.add_argument("--variants", default="5,0,6,7,8")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--d", type=int, default=64)
     args = ap.parse_args()
@@ -41,10 +41,14 @@ def main():
             deg = adj.indptr[1:] - adj.indptr[:-1]
             print("shape %s nnz %d gen %.1fs build %.1fs chunk %d heavy_rows %d chunks %d maxdeg %d" % (
                 shape, nnz, t1 - t0, t2 - t1, adj.chunk_nnz, adj.desc.n_heavy_rows, adj.desc.n_chunks, int(deg.max())), flush=True)
+            _lib.check(_lib.lib().hgr_set_spmm_variant(5))
+            y_ref = ops.spmm_raw(adj, x).clone()
             for variant in (int(v) for v in args.variants.split(",")):
                 _lib.check(_lib.lib().hgr_set_spmm_variant(variant))
                 for _ in range(3):
                     y = ops.spmm_raw(adj, x)
+                if not torch.equal(y, y_ref):
+                    print("  variant %d: RESULT DIFFERS from the static kernel (max abs %.3e)" % (variant, float((y - y_ref).abs().max())))
                 times = []
                 for _ in range(args.iters):
                     flush.fill_(1)
