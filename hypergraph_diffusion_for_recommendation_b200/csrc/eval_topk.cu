@@ -15,7 +15,7 @@
 //                            warp 0: bulk-copy producer (6-stage mbarrier ring); warp 1: one thread issues
 //                            tcgen05.mma kind::f16 (bf16 x bf16 -> fp32, M128 N128 K16, 4 per half) into a
 //                            double-buffered TMEM accumulator (2 stages x 2 halves x 128 columns = 512);
-//                            warps 2..9: epilogue, tcgen05.ld 32x32b (thread = user row), the user's training
+//                            warps 2..17: epilogue, tcgen05.ld 32x32b (thread = user row x 64-column half), the user's training
 //                            items poisoned to NaN by walking the train CSR row in step with the columns.
 //        SAMPLE pass         over 1/4 of the item tiles: 32 running bucket maxima per (user, item segment).
 //        eval_tau_kernel     K-th largest bucket maximum = a lower bound tau of the user's K-th best score.
@@ -47,8 +47,9 @@ constexpr int EV_STAGES = 4;       // item tiles in flight (192 KB of shared mem
                                    // 512-column TMEM allocation never waits)
 constexpr int EV_A_BYTES = EV_BM * EV_D * 2;        // 32 KB per bf16 term (hi, lo)
 constexpr int EV_B_BYTES = EV_BN * EV_D * 2;        // 16 KB per bf16 term (hi, lo)
-constexpr int EV_EPI_WARPS = 8;
-constexpr int EV_THREADS = 64 + 32 * EV_EPI_WARPS;  // producer warp, MMA warp, 8 epilogue warps
+constexpr int EV_CSPLIT = 2;                        // epilogue warps per (128-row half, TMEM lane quadrant): column halves of a tile
+constexpr int EV_EPI_WARPS = 8 * EV_CSPLIT;         // 4 per scheduler: the epilogue is latency-bound with fewer
+constexpr int EV_THREADS = 64 + 32 * EV_EPI_WARPS;  // producer warp, MMA warp, 16 epilogue warps
 constexpr int EV_TMEM_COLS = 512;
 constexpr int EV_SAMPLE_STRIDE = 4;                 // the sample pass scores 1 / 4 of the item tiles
 constexpr int EV_BUCKETS = 32;                      // bucket maxima per (user, sample segment)
@@ -72,10 +73,10 @@ struct EvalParams {
     const int32_t *test_users;
     const int64_t *train_indptr;
     const int32_t *train_indices;
-    float *bucket_max;   // SAMPLE out: [n_segments][n_test_pad][EV_BUCKETS]
+    float *bucket_max;   // SAMPLE out: [n_segments * EV_CSPLIT][n_test_pad][EV_BUCKETS]
     const float *thr;    // FILTER in:  [n_test_pad] tau - 2 eps (-inf: no bound)
-    float2 *cand;        // FILTER out: [n_splits][n_test_pad][cap] (approx score, item id bits)
-    int32_t *cand_cnt;   // [n_splits][n_test_pad]
+    float2 *cand;        // FILTER out: [n_splits * EV_CSPLIT][n_test_pad][cap] (approx score, item id bits)
+    int32_t *cand_cnt;   // [n_splits * EV_CSPLIT][n_test_pad]
     int32_t *overflow;   // [n_test_pad] flag; [n_test_pad] = count, [n_test_pad + 1 ...] = list of flagged rows
     int32_t n_test, n_items, n_tiles;
     int32_t tiles_per_cta;  // tiles a CTA scores
@@ -218,7 +219,7 @@ __device__ __forceinline__ void ev_poison(uint32_t (&v)[32], int col0, int n_ite
     unsigned mb = 0;
     if (nt0 < col0 + 32) {
         do {
-            mb |= 1u << (nt0 - col0);
+            if (nt0 >= col0) mb |= 1u << (nt0 - col0);  // items below col0 lie in columns another warp examines
             nt0 = nt1;
             ++tp;
             nt1 = tp + 1 < tend ? __ldg(train_indices + tp + 1) : INT_MAX;
@@ -263,8 +264,8 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, part = blockIdx.y;
-    const int tile0 = part * P.tile_pitch;
+    const int m_blk = blockIdx.x;
+    const int tile0 = blockIdx.y * P.tile_pitch;
     const int n_my = max(0, min(P.tiles_per_cta, P.n_tiles - tile0));
 
     const uint32_t bar_full = smem_u32(&bars[0]);               // [EV_STAGES]
@@ -347,10 +348,12 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
             }
         }
     } else {
-        // ===== epilogue: 8 warps, thread = one user row of one 128-row half =====
+        // ===== epilogue: 16 warps; thread = one user row of one 128-row half x one 64-column half of every tile =====
         const int ew = warp - 2;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-        const int half = ew >> 2;
+        const int half = (ew >> 2) & 1;
+        const int chalf = ew >> 3;
+        const int part = blockIdx.y * EV_CSPLIT + chalf;  // slice of the candidate / bucket arrays this thread fills
         const int64_t row = (int64_t)m_blk * EV_BM + half * 128 + quad * 32 + lane;
         const bool live = row < P.n_test;
         const int64_t n_pad = (int64_t)gridDim.x * EV_BM;
@@ -390,44 +393,36 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + half * 128);
             const int col_tile = (tile0 + it) * EV_BN;
-            // two register buffers: the TMEM load of the next 32 columns is in flight while these are examined.
-            // The chunk loop is unrolled by 2 only: the body is large and an instruction-cache miss costs more
-            // than the loop overhead.
-            uint32_t va[32], vb[32];
-            tc_ld32(tcol, va);
+            // this warp's 64 columns of the tile as two 32-column TMEM loads; four epilogue warps per scheduler hide
+            // the load latency, so there is a single register buffer (the kernel must stay under 112 registers)
 #pragma unroll 1
-            for (int c2 = 0; c2 < EV_BN / 32; c2 += 2) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = chalf * 2 + cc;
+                uint32_t v[32];
+                tc_ld32(tcol + c * 32, v);
+                tc_ld_wait();
+                const int col0 = col_tile + c * 32;
+                if (nt0 < col0 + 32 || col0 + 32 > P.n_items) ev_poison(v, col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
+                if (MODE == EV_SAMPLE) {
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t(&v)[32] = cc ? vb : va;
-                    uint32_t(&nx)[32] = cc ? va : vb;
-                    const int c = c2 + cc;
-                    tc_ld_wait();
-                    if (c + 1 < EV_BN / 32) tc_ld32(tcol + (c + 1) * 32, nx);
-                    const int col0 = col_tile + c * 32;
-                    if (nt0 < col0 + 32 || col0 + 32 > P.n_items)
-                        ev_poison(v, col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
-                    if (MODE == EV_SAMPLE) {
+                    for (int j = 0; j < 32; ++j) bm[j] = fmaxf(bm[j], __uint_as_float(v[j]));
+                } else {
+                    // group maxima first: a user row meets its threshold in ~1 of 30 chunks, and then usually
+                    // in a single group of 4 columns
+                    float m4[8];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) bm[j] = fmaxf(bm[j], __uint_as_float(v[j]));
-                    } else {
-                        // group maxima first: a user row meets its threshold in ~1 of 20 chunks, and then usually
-                        // in a single group of 4 columns
-                        float m4[8];
+                    for (int g = 0; g < 8; ++g)
+                        m4[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
+                                      fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+                    const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
+                                          fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+                    if (m >= thr) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
-                            m4[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
-                                          fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-                        const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
-                                              fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
-                        if (m >= thr) {
-#pragma unroll
-                            for (int g = 0; g < 8; ++g)
-                                if (m4[g] >= thr)
-                                    cnt = ev_append4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                                     __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]), thr,
-                                                     col0 + 4 * g, cnt, P.cap, crow);
-                        }
+                            if (m4[g] >= thr)
+                                cnt = ev_append4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                 __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]), thr,
+                                                 col0 + 4 * g, cnt, P.cap, crow);
                     }
                 }
             }
@@ -506,21 +501,30 @@ __global__ void __launch_bounds__(128) eval_tau_kernel(const float *__restrict__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + warp;
     if (row >= n_test) return;
-    unsigned long long keys[16];  // n_seg <= 16 (make_plan)
+    // Up to 16 bucket maxima per lane are merged down to 4 (the maximum of a group of buckets is the score of one
+    // item of the union bucket): 128 disjoint buckets over the whole sample, a K-th largest within 1-2 ranks of the one
+    // over 512 buckets at a quarter of the selection work.
+    const int per = (n_seg + 3) / 4;
+    unsigned long long keys[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
-        keys[s] = 0ull;
         if (s < n_seg) {
             const float v = bucket_max[((int64_t)s * n_pad + row) * EV_BUCKETS + lane];
-            if (v > -CUDART_INF_F) keys[s] = rank_key(v, s * EV_BUCKETS + lane);  // false for NaN and for empty buckets
+            if (v > -CUDART_INF_F) {  // false for NaN and for empty buckets
+                const unsigned long long k = rank_key(v, s * EV_BUCKETS + lane);
+                const int q = s / per;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (m == q && k > keys[m]) keys[m] = k;
+            }
         }
     }
     unsigned long long prev = ~0ull, best = 0ull;
     for (int r = 0; r < K; ++r) {
         best = 0ull;
 #pragma unroll
-        for (int s = 0; s < 16; ++s)
-            if (keys[s] < prev && keys[s] > best) best = keys[s];
+        for (int m = 0; m < 4; ++m)
+            if (keys[m] < prev && keys[m] > best) best = keys[m];
         best = warp_max_u64(best);
         if (best == 0ull) break;
         prev = best;
@@ -574,16 +578,38 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
         base += cnt;
     }
     __syncwarp();
+    // K-th best approximate key.  Small lists (the usual case): every lane counts how many keys beat each of its own
+    // (keys are unique: the id is part of the key), the key beaten by exactly K - 1 others is the answer.
     unsigned long long prev = ~0ull, best = 0ull;
-    for (int r = 0; r < K; ++r) {
-        best = 0ull;
-        for (int j = lane; j < n_c; j += 32) {
-            const unsigned long long k = keys[warp][j];
-            if (k < prev && k > best) best = k;
+    if (n_c <= 256) {
+        unsigned long long mine[8];
+        int beat[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            mine[q] = lane + 32 * q < n_c ? keys[warp][lane + 32 * q] : 0ull;
+            beat[q] = 0;
         }
-        best = warp_max_u64(best);
-        if (best == 0ull) break;
-        prev = best;
+        for (int j = 0; j < n_c; ++j) {
+            const unsigned long long k = keys[warp][j];  // broadcast read
+#pragma unroll
+            for (int q = 0; q < 8; ++q) beat[q] += k > mine[q];
+        }
+        unsigned long long kth = 0ull;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (lane + 32 * q < n_c && beat[q] == K - 1) kth = mine[q];
+        best = warp_max_u64(kth);  // 0 when the list holds fewer than K keys
+    } else {
+        for (int r = 0; r < K; ++r) {
+            best = 0ull;
+            for (int j = lane; j < n_c; j += 32) {
+                const unsigned long long k = keys[warp][j];
+                if (k < prev && k > best) best = k;
+            }
+            best = warp_max_u64(best);
+            if (best == 0ull) break;
+            prev = best;
+        }
     }
     // (b) + (c): keep keys >= (tau_a - 2 eps), re-score them, compact in place (slot <= source index)
     unsigned long long keep_key = 0ull;
@@ -623,24 +649,48 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
         // observed error in parts per million of the bound eps = slack / 2 (must stay below 1e6)
         atomicMax(stats + 3, (unsigned long long)(worst / (0.5f * slack[row]) * 1.0e6f));
     }
-    // (d) K rounds: best exact key strictly below the previous winner
-    prev = ~0ull;
+    // (d) exact top-K.  Few survivors (the usual case): the rank of a key = the number of keys that beat it = its
+    // position in the list; otherwise K rounds of "best key strictly below the previous winner".
     int filled = 0;
-    for (int r = 0; r < K; ++r) {
-        best = 0ull;
-        for (int j = lane; j < n_keep; j += 32) {
+    if (n_keep <= 64) {
+        __syncwarp();
+        const unsigned long long m0 = lane < n_keep ? keys[warp][lane] : 0ull;
+        const unsigned long long m1 = lane + 32 < n_keep ? keys[warp][lane + 32] : 0ull;
+        int b0 = 0, b1 = 0;
+        for (int j = 0; j < n_keep; ++j) {
             const unsigned long long k = keys[warp][j];
-            if (k < prev && k > best) best = k;
+            b0 += k > m0;
+            b1 += k > m1;
         }
-        best = warp_max_u64(best);
-        if (best == 0ull) break;
-        prev = best;
-        if (lane == 0) {
-            const uint32_t ob = (uint32_t)(best >> 32);
-            out_ids[row * K + r] = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffu));
-            out_scores[row * K + r] = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+        if (lane < n_keep && b0 < K) {
+            const uint32_t ob = (uint32_t)(m0 >> 32);
+            out_ids[row * K + b0] = (int32_t)(0xffffffffu - (uint32_t)(m0 & 0xffffffffu));
+            out_scores[row * K + b0] = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
         }
-        ++filled;
+        if (lane + 32 < n_keep && b1 < K) {
+            const uint32_t ob = (uint32_t)(m1 >> 32);
+            out_ids[row * K + b1] = (int32_t)(0xffffffffu - (uint32_t)(m1 & 0xffffffffu));
+            out_scores[row * K + b1] = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+        }
+        filled = n_keep < K ? n_keep : K;
+    } else {
+        prev = ~0ull;
+        for (int r = 0; r < K; ++r) {
+            best = 0ull;
+            for (int j = lane; j < n_keep; j += 32) {
+                const unsigned long long k = keys[warp][j];
+                if (k < prev && k > best) best = k;
+            }
+            best = warp_max_u64(best);
+            if (best == 0ull) break;
+            prev = best;
+            if (lane == 0) {
+                const uint32_t ob = (uint32_t)(best >> 32);
+                out_ids[row * K + r] = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffu));
+                out_scores[row * K + r] = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+            }
+            ++filled;
+        }
     }
     // fewer than K unmasked items in the whole catalogue: the reference then returns masked items
     // (-10e8) in ascending id order (oracle topk_exact keeps them as candidates)
@@ -789,7 +839,7 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
     p.n_test_pad = ceil_div(n_test > 0 ? n_test : 1, EV_BM) * EV_BM;
     p.n_items_pad = ceil_div(n_items > 0 ? n_items : 1, EV_BN) * EV_BN;
     p.n_tiles = (int)(p.n_items_pad / EV_BN);
-    p.cap = K <= 32 ? 512 : 1024;
+    p.cap = K <= 32 ? 256 : 512;  // per (split, column half)
     const int64_t m_blocks = p.n_test_pad / EV_BM;
     // filter pass: enough CTAs to fill 148 SMs about twice, at least 8 tiles per CTA
     int splits = (int)ceil_div(2 * 148, m_blocks);
@@ -803,7 +853,7 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
     // at least 4 segments (128 buckets >= K), more when few user blocks would leave SMs idle
     int seg = (int)ceil_div(2 * 148, m_blocks);
     if (seg < 4) seg = 4;
-    if (seg > 16) seg = 16;
+    if (seg > 8) seg = 8;  // eval_tau_kernel holds n_seg * EV_CSPLIT <= 16 keys per lane
     if (seg > p.n_tiles) seg = p.n_tiles;
     p.seg_pitch = p.n_tiles / seg;
     p.n_seg = seg;
@@ -816,10 +866,10 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
         p.off_bp = o; o = align_up(o + (size_t)p.n_items_pad * EV_D * 2 * 2, 256);
         p.off_slack = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
         p.off_maxnorm = o; o = align_up(o + 256, 256);
-        p.off_bucket = o; o = align_up(o + (size_t)p.n_seg * p.n_test_pad * EV_BUCKETS * 4, 256);
+        p.off_bucket = o; o = align_up(o + (size_t)p.n_seg * EV_CSPLIT * p.n_test_pad * EV_BUCKETS * 4, 256);
         p.off_thr = o; o = align_up(o + (size_t)p.n_test_pad * 4, 256);
-        p.off_cand = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * p.cap * 8, 256);
-        p.off_cnt = o; o = align_up(o + (size_t)p.n_splits * p.n_test_pad * 4, 256);
+        p.off_cand = o; o = align_up(o + (size_t)p.n_splits * EV_CSPLIT * p.n_test_pad * p.cap * 8, 256);
+        p.off_cnt = o; o = align_up(o + (size_t)p.n_splits * EV_CSPLIT * p.n_test_pad * 4, 256);
     }
     p.off_overflow = o; o = align_up(o + (size_t)(2 * p.n_test_pad + 1) * 4, 256);
     p.off_scratch = o; o = align_up(o + (size_t)p.n_brute_blocks * (size_t)(n_items > 0 ? n_items : 1) * 4, 256);
@@ -910,15 +960,15 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
         P.tile_pitch = p.seg_pitch;
         eval_scores_kernel<EV_SAMPLE><<<dim3(m_blocks, (unsigned)p.n_seg), EV_THREADS, smem, st>>>(P);
         HGR_LAUNCH_OK("eval_scores_kernel<sample>");
-        eval_tau_kernel<<<(unsigned)ceil_div(n_test, 4), 128, 0, st>>>(P.bucket_max, p.n_seg, p.n_test_pad, (int)n_test, K, slack, thr);
+        eval_tau_kernel<<<(unsigned)ceil_div(n_test, 4), 128, 0, st>>>(P.bucket_max, p.n_seg * EV_CSPLIT, p.n_test_pad, (int)n_test, K, slack, thr);
         HGR_LAUNCH_OK("eval_tau_kernel");
         P.tiles_per_cta = p.tiles_per_split;
         P.tile_pitch = p.tiles_per_split;
         eval_scores_kernel<EV_FILTER><<<dim3(m_blocks, (unsigned)p.n_splits), EV_THREADS, smem, st>>>(P);
         HGR_LAUNCH_OK("eval_scores_kernel<filter>");
         eval_rescore_kernel<<<(unsigned)ceil_div(n_test, RS_WARPS), RS_WARPS * 32, 0, st>>>(
-            user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, slack, overflow, p.n_splits,
-            p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
+            user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, slack, overflow,
+            p.n_splits * EV_CSPLIT, p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
         HGR_LAUNCH_OK("eval_rescore_kernel");
     }
     eval_brute_kernel<<<(unsigned)p.n_brute_blocks, BF_THREADS, 0, st>>>(user_emb, item_emb, D, (int)n_items, test_users,
