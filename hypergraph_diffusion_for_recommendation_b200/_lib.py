@@ -8,6 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libhgr.so")
 
 HGR_MAX_ADDENDS = 8
+HGR_MAX_GATHER = 8
 
 
 class HgrError(RuntimeError):
@@ -33,6 +34,7 @@ class Epilogue(C.Structure):
         ("n_addends", C.c_int32), ("addends", C.c_void_p * HGR_MAX_ADDENDS),
         ("scale", C.c_float), ("scale_always", C.c_int32),
         ("pre", C.c_void_p),
+        ("n_gather", C.c_int32), ("gather_out", C.c_void_p * HGR_MAX_GATHER), ("gather_row_offset", C.c_int64),
     ]
 
 

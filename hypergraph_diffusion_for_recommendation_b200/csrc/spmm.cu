@@ -220,7 +220,15 @@ __device__ __forceinline__ void finish_row(float4 acc, int64_t row, int gl, unsi
         acc.z *= ep.scale;
         acc.w *= ep.scale;
     }
-    reinterpret_cast<float4 *>(Y)[off] = acc;
+    if (Y) reinterpret_cast<float4 *>(Y)[off] = acc;
+    if (ep.n_gather > 0) {
+        // fused all-gather: the same row into the gathered table of every rank (peer-mapped memory; plain 128-bit
+        // stores travel over NVLink as posted writes while the block moves on to its next rows)
+        const int64_t goff = (ep.gather_row_offset + row) * LPR + gl;
+#pragma unroll
+        for (int p = 0; p < HGR_MAX_GATHER; ++p)  // constant indices keep ep in param space
+            if (p < ep.n_gather) reinterpret_cast<float4 *>(ep.gather_out[p])[goff] = acc;
+    }
 }
 
 // grid = [heavy chunk blocks | light row blocks]
@@ -327,6 +335,10 @@ static int check_epilogue(const hgr_epilogue_t *ep) {
                 "epilogue: operands must be 16-byte aligned");
     for (int j = 0; j < ep->n_addends; ++j)
         HGR_REQUIRE(ep->addends[j] && aligned16(ep->addends[j]), "epilogue: addend %d NULL or misaligned", j);
+    HGR_REQUIRE(ep->n_gather >= 0 && ep->n_gather <= HGR_MAX_GATHER, "epilogue: n_gather %d out of range", ep->n_gather);
+    for (int j = 0; j < ep->n_gather; ++j)
+        HGR_REQUIRE(ep->gather_out[j] && aligned16(ep->gather_out[j]), "epilogue: gather_out %d NULL or misaligned", j);
+    HGR_REQUIRE(ep->gather_row_offset >= 0, "epilogue: negative gather_row_offset");
     return HGR_OK;
 }
 
@@ -395,7 +407,7 @@ static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, co
     rc = check_epilogue(epi);
     if (rc) return rc;
     HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
-    HGR_REQUIRE(A->n_rows == 0 || (X && Y), "X or Y is NULL");
+    HGR_REQUIRE(A->n_rows == 0 || (X && (Y || (epi && epi->n_gather > 0))), "X or Y is NULL");
     HGR_REQUIRE(aligned16(X) && aligned16(Y), "X and Y must be 16-byte aligned");
     const size_t need = hgr_spmm_workspace_bytes(A, D);
     if (need > 0 && (ws == nullptr || ws_bytes < need))

@@ -9,8 +9,12 @@ The reference is single-process; this module is the scaling axis 
 * **Local matrix.**  ``A_loc = A[own rows, :]`` with columns renumbered by ``perm`` but kept in their
   ORIGINAL ascending order inside a row, so each output row is accumulated in exactly the order of the
   single-GPU kernel: the sharded result is bit-identical to the unsharded one.
-* **Exchange.**  One ``all_gather`` of the owned rows per propagation (NCCL over NVLink 5 / NVSwitch), then the
-  same ``hgr_spmm_f32`` kernel on ``A_loc``.  The normalised adjacency is symmetric, so the backward pass is
+* **Exchange.**  Every propagation needs the gathered table of the previous one.  Fused form (default on CUDA): the
+  propagation kernel's epilogue stores each finished row into the gathered table of EVERY rank -- symmetric-memory
+  buffers mapped over NVLink (``hgr_epilogue_t::gather_out``) -- so the all-gather rides on the kernel that produces
+  the rows and overlaps its remaining work; a device-side barrier orders the readers.  Rows that do not come out of a
+  propagation kernel (parameters, outputs of dense layers) use one NCCL ``all_gather``.  Then the same
+  ``hgr_spmm_f32`` kernel on ``A_loc``.  The normalised adjacency is symmetric, so the backward pass is
   ``dX_own = A_loc . all_gather(dY_own)``: a gather, never a reduction.
 * **Loss.**  The final tables are gathered once; every rank evaluates the fused BPR + L2 kernel on the whole
   batch (identical numbers on all ranks), so the gradient of the gather is a slice.  Gradients of the small
@@ -107,17 +111,44 @@ class LibhgrKernels:
         return DeviceCSR(indptr, indices, values, shape)  # rows are long-tailed like the global matrix: split plan kept
 
     @staticmethod
-    def spmm(block, x, ep=None):
+    def spmm(block, x, ep=None, no_local_out=False):
         """``epilogue(block @ x)``; ``ep`` is a dict of ``ops.make_epilogue`` keyword arguments."""
         from . import ops
 
-        return ops.spmm_raw(block, x, ops.make_epilogue(**ep) if ep else None)
+        return ops.spmm_raw(block, x, ops.make_epilogue(**ep) if ep else None, no_local_out=no_local_out)
 
     @staticmethod
     def leaky_ln_bwd(pre, dy, gamma, eps, slope):
         from . import ops
 
         return ops.leaky_ln_bwd(pre, dy, gamma, eps, slope)
+
+
+class SymmetricPool:
+    """Ring of gathered ``[world * n_loc, D]`` tables in symmetric memory: every rank allocates the same buffers,
+    ``rendezvous`` maps the peers' copies into this process (NVLink peer access), and the propagation kernel's
+    epilogue stores each finished row straight into all of them (``hgr_epilogue_t::gather_out``).  ``barrier``
+    is the device-side cross-rank barrier that orders the peers' reads after those stores."""
+
+    def __init__(self, n_glob: int, d: int, device, group, n_buffers: int = 4):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.bufs, self.hdls, self.ptrs = [], [], []
+        for _ in range(n_buffers):
+            t = symm_mem.empty((n_glob, d), dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+            self.bufs.append(t)
+            self.hdls.append(h)
+            self.ptrs.append([int(p) for p in h.buffer_ptrs])
+        self.next = 0
+
+    def take(self) -> int:
+        k = self.next
+        self.next = (k + 1) % len(self.bufs)
+        return k
+
+    def barrier(self, k: int) -> None:
+        self.hdls[k].barrier(channel=0)
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -143,12 +174,12 @@ class _DistSpmm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, g):
         ctx.g = g
-        return g.k.spmm(g.block, g.all_gather(x))
+        return g.k.spmm(g.block, g.gathered(x.contiguous()))
 
     @staticmethod
     def backward(ctx, dy):
         g = ctx.g  # A symmetric: dX_own = (A^T dY)[own] = A[own, :] dY
-        return g.k.spmm(g.block, g.all_gather(dy.contiguous())), None
+        return g.k.spmm(g.block, g.gathered(dy.contiguous())), None
 
 
 class DistGraph:
@@ -164,6 +195,14 @@ class DistGraph:
         self.device = indptr.device
         self._nnz_local = int(indices.numel())
         self.gather_events = None  # bench: list of (start, end) CUDA events around every all_gather
+        # fused all-gather (propagation epilogue stores into every rank's gathered table): CUDA + libhgr only
+        import os
+
+        self.fused = (self.k is LibhgrKernels and self.world > 1 and indptr.is_cuda and self.world <= 8
+                      and os.environ.get("HGR_FUSED_GATHER", "1") != "0")
+        self._pools = {}     # D -> SymmetricPool
+        self._published = {}  # pool slot -> (tensor kept alive, version): local rows whose gathered copy sits in that slot
+        self.n_fused, self.n_collective = 0, 0
 
     def _nnz(self):
         return self._nnz_local
@@ -176,7 +215,46 @@ class DistGraph:
 
     cuda = to
 
+    # ---- fused all-gather ---------------------------------------------------------------------
+    def pool(self, d: int):
+        p = self._pools.get(d)
+        if p is None and self.fused:
+            try:
+                p = SymmetricPool(self.part.n_glob, d, self.device, self.group)
+            except Exception as e:  # no peer access / symmetric memory on this box: keep the NCCL exchange
+                import warnings
+
+                warnings.warn("symmetric memory unavailable (%s): sharded propagation falls back to NCCL all_gather" % (e,))
+                self.fused = False
+                return None
+            self._pools[d] = p
+        return p
+
+    def spmm_published(self, full_in: torch.Tensor, ep: dict | None = None, want_local: bool = True):
+        """``y_own = epilogue(A_loc @ full_in)`` whose rows are stored, by the kernel's own epilogue, into slot ``k`` of
+        the symmetric pool on EVERY rank (fused all-gather).  Returns ``(gathered [n_glob, D], y_own or None)``."""
+        pool = self.pool(full_in.shape[1])
+        k = pool.take()
+        self._published.pop(k, None)  # the slot is being rewritten: forget what it held
+        ep = dict(ep or {}, gather_ptrs=pool.ptrs[k], gather_row_offset=self.rank * self.part.n_loc)
+        y = self.k.spmm(self.block, full_in, ep, no_local_out=not want_local)
+        pool.barrier(k)  # every rank's rows have landed here, and every rank is done reading the slot's old contents
+        if y is not None:
+            self._published[k] = (y, y._version)
+        self.n_fused += 1
+        return pool.bufs[k], y
+
+    def gathered(self, x: torch.Tensor) -> torch.Tensor:
+        """Gathered table of the owned rows ``x``: the pool slot a previous propagation already filled, else a collective."""
+        if self.fused:
+            pool = self._pools.get(x.shape[1])
+            for k, (t, ver) in self._published.items():
+                if t is x or (t.data_ptr() == x.data_ptr() and t.shape == x.shape and t._version == ver == x._version):
+                    return pool.bufs[k]
+        return self.all_gather(x)
+
     def all_gather(self, x: torch.Tensor) -> torch.Tensor:
+        self.n_collective += 1
         x = x.contiguous()
         out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         if self.gather_events is not None and x.is_cuda:
@@ -210,10 +288,14 @@ def _lightgcn_rows(g: DistGraph, e0, n_layers, sum_readout):
         return e0.clone()
     layers = [e0]
     cur = e0
+    full = g.gathered(e0)
     for k in range(n_layers):
-        full = g.all_gather(cur)
         if k + 1 < n_layers:
-            cur = g.k.spmm(g.block, full)
+            if g.fused and g.pool(e0.shape[1]) is not None:
+                full, cur = g.spmm_published(full, None, want_local=True)  # next layer's input arrives with this kernel
+            else:
+                cur = g.k.spmm(g.block, full)
+                full = g.all_gather(cur)
             layers.append(cur)
         else:
             cur = g.k.spmm(g.block, full, dict(addends=layers, scale=1.0 if sum_readout else 1.0 / (n_layers + 1)))
@@ -239,12 +321,20 @@ class _DistHGConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, residual, g, slope, eps):
         need_pre = (slope is not None or gamma is not None) and any(ctx.needs_input_grad[:3])
-        t = g.k.spmm(g.block, g.all_gather(x.contiguous()))
-        pre = torch.empty_like(t) if need_pre else None
+        x = x.contiguous()
+        pre = torch.empty_like(x) if need_pre else None
         gm = gamma.contiguous() if gamma is not None else None
         bt = beta.contiguous() if beta is not None else None
         rs = residual.contiguous() if residual is not None else None
-        y = g.k.spmm(g.block, g.all_gather(t), dict(slope=slope, gamma=gm, beta=bt, eps=eps, residual=rs, pre=pre))
+        ep = dict(slope=slope, gamma=gm, beta=bt, eps=eps, residual=rs, pre=pre)
+        if g.fused and g.pool(x.shape[1]) is not None:
+            # node -> hyperedge stage publishes its rows into every rank's table; the node stage publishes y too,
+            # for the propagation that consumes it next (EquivSetConv chains two of these)
+            full_t, _ = g.spmm_published(g.gathered(x), None, want_local=False)
+            _, y = g.spmm_published(full_t, ep, want_local=True)
+        else:
+            t = g.k.spmm(g.block, g.all_gather(x))
+            y = g.k.spmm(g.block, g.all_gather(t), ep)
         ctx.g, ctx.slope, ctx.eps = g, slope, eps
         ctx.has_ln, ctx.has_res = gamma is not None, residual is not None
         ctx.save_for_backward(pre, gm)
@@ -262,8 +352,12 @@ class _DistHGConv(torch.autograd.Function):
             dz = dy
         dx = None
         if ctx.needs_input_grad[0]:
-            t = g.k.spmm(g.block, g.all_gather(dz))
-            dx = g.k.spmm(g.block, g.all_gather(t))
+            if g.fused and g.pool(dz.shape[1]) is not None:
+                full_t, _ = g.spmm_published(g.gathered(dz), None, want_local=False)
+                dx = g.k.spmm(g.block, full_t)
+            else:
+                t = g.k.spmm(g.block, g.all_gather(dz))
+                dx = g.k.spmm(g.block, g.all_gather(t))
         return dx, dgamma, dbeta, (dy if ctx.has_res else None), None, None, None
 
 

@@ -56,7 +56,7 @@ def _check_dense(x: torch.Tensor, rows: int, what: str) -> torch.Tensor:
 
 
 def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addends=(), scale=1.0, scale_always=False,
-              pre=None) -> _lib.Epilogue:
+              pre=None, gather_ptrs=(), gather_row_offset=0) -> _lib.Epilogue:
     ep = _lib.Epilogue()
     ep.use_leaky = 0 if slope is None else 1
     ep.leaky_slope = 0.0 if slope is None else float(slope)
@@ -67,6 +67,10 @@ def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addend
         ep.addends[j] = a.data_ptr()
     ep.scale, ep.scale_always = float(scale), int(bool(scale_always))
     ep.pre = _lib.ptr(pre)
+    ep.n_gather = len(gather_ptrs)  # fused all-gather: raw (peer-mapped) device pointers of every rank's gathered table
+    for j, p in enumerate(gather_ptrs):
+        ep.gather_out[j] = int(p)
+    ep.gather_row_offset = int(gather_row_offset)
     return ep
 
 
@@ -98,14 +102,19 @@ def _ws(a: DeviceCSR, d: int):
     return (None, 0) if ws is None else (ws.data_ptr(), ws.numel() * 4)
 
 
-def spmm_raw(a: DeviceCSR, x: torch.Tensor, ep: _lib.Epilogue | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """One ``hgr_spmm_f32`` call; no autograd."""
+def spmm_raw(a: DeviceCSR, x: torch.Tensor, ep: _lib.Epilogue | None = None, out: torch.Tensor | None = None,
+             no_local_out: bool = False):
+    """One ``hgr_spmm_f32`` call; no autograd.  ``no_local_out``: the epilogue's fused all-gather is the only
+    destination (returns None)."""
     x = _check_dense(x, a.shape[1], "X")
     d = x.shape[1]
-    y = out if out is not None else torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
+    if no_local_out:
+        y = None
+    else:
+        y = out if out is not None else torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
     ws, ws_bytes = _ws(a, d)
     with _Timed(1):
-        _lib.check(_lib.lib().hgr_spmm_f32(C.byref(a.desc), x.data_ptr(), y.data_ptr(), d, None if ep is None else C.byref(ep),
+        _lib.check(_lib.lib().hgr_spmm_f32(C.byref(a.desc), x.data_ptr(), _lib.ptr(y), d, None if ep is None else C.byref(ep),
                                            ws, ws_bytes, _lib.stream_ptr()))
     return y
 

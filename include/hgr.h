@@ -71,9 +71,10 @@ typedef struct {
  *   acc       = LayerNorm(acc) * gamma + beta         lns[k](...), HGNN_HD3.py:421,710,714
  *   acc      += residual[row]                         "+ res" / "+ Xve", same lines
  *   acc       = (acc + sum_j addend[j][row]) * scale  layer mean/sum readout, LightGCN.py:135-136
- *   y[row]    = acc
+ *   y[row]    = acc                                   (+ the same row into every gather_out table)
  */
 #define HGR_MAX_ADDENDS 8
+#define HGR_MAX_GATHER 8
 typedef struct {
     int32_t use_leaky;
     float leaky_slope;
@@ -86,6 +87,14 @@ typedef struct {
     float scale;                           /* applied only when n_addends > 0 or scale_always != 0 */
     int32_t scale_always;
     float *pre;                            /* [n_rows, D] or NULL */
+    /* Fused all-gather (multi-GPU, dist.py): the finished row is ALSO stored at row
+     * gather_row_offset + row of every table in gather_out -- the gathered [world * n_loc, D] buffers of
+     * all ranks, peer-mapped over NVLink (symmetric memory) -- so the exchange that follows a sharded
+     * propagation rides on the kernel's own epilogue instead of a separate collective.  y may then be
+     * NULL.  The caller orders the peers' reads after the kernel with a cross-rank barrier. */
+    int32_t n_gather;
+    float *gather_out[HGR_MAX_GATHER];
+    int64_t gather_row_offset;
 } hgr_epilogue_t;
 
 /* Y[n_rows, D] = epilogue(A . X[n_cols, D]).  Replaces torch.sparse.mm(adj, X)
