@@ -231,8 +231,15 @@ def run_ours(args):
     model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
     optimizer = torch.optim.Adam(model.parameters(), lr=LR, fused=True)
 
-    # triples for every step: positives from the training list, uniform negatives (device sampler is a
-    # "next" row of SURVEY.md 8f; parity runs replay the reference sampler's triples instead)
+    # triples: the device sampler (csrc/sampler.cu: shuffled positives + rejection-sampled negatives, the body of
+    # util/sampler.py:237-264) runs INSIDE every device-timed step; the e2e leg replays host-resident triples, the
+    # interface of the reference's sampler (CPU LongTensors).  Every rank draws the same batch (same seed).
+    from hypergraph_diffusion_for_recommendation_b200.sampler import PairwiseSampler
+
+    sampler = PairwiseSampler(u, i, U, I, device=dev, seed=99)
+    sgen = torch.Generator(device=dev)
+    sgen.manual_seed(1234)
+    perm = torch.randperm(int(u.numel()), device=dev, generator=sgen)
     n_steps = args.warmup + args.steps
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)  # the same batch on every rank: the sharded step evaluates the loss on the whole batch (dist.py)
@@ -286,7 +293,8 @@ def run_ours(args):
                 losses = step(tri)
                 host_losses = losses.tolist()  # D2H of the step's result, like the reference's .item() calls
             else:
-                losses = step(dev_triples[s])
+                off = (s * B) % max(int(perm.numel()) - B, 1)
+                losses = step(sampler.batch(perm, off, min(B, int(perm.numel()))))
             if small:
                 e1.record()
                 per_step.append((e0, e1))

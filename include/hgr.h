@@ -241,6 +241,21 @@ int hgr_ssl_loss_fwd_f32(const float *E1, const float *E2, int64_t n_rows1, int6
 int hgr_ssl_loss_bwd_f32(int64_t n_rows1, int64_t n_rows2, int32_t D, const int64_t *nodes, int64_t M, float temp, int32_t normalize,
                          void *saved, size_t saved_bytes, const float *grad_out, float *dE1, float *dE2, hgr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * BPR negative sampling on the device: the body of next_batch_pairwise (util/sampler.py:237-264).
+ * Positives of the batch are training pairs perm[perm_offset .. perm_offset + batch) of (edge_u, edge_i)
+ * (perm == NULL: the pairs themselves in stored order); for each, n_negs items drawn uniformly from
+ * [0, n_items) and re-drawn while they are in the user's training row (train_indptr / train_indices, columns
+ * ascending).  out_u, out_p: int64 [batch]; out_n: int64 [batch * n_negs] (the reference's j_idx order).
+ * Philox4x32-10(seed) with counter (stream_offset + sample index, attempt): reproducible, independent of the
+ * launch geometry; pass a different stream_offset (e.g. the number of samples drawn so far) for every batch.
+ * *gave_up (device int, optional, caller zeroes) counts samples still colliding after 256 draws.
+ * ------------------------------------------------------------------------------------------- */
+int hgr_bpr_sample(const int32_t *edge_u, const int32_t *edge_i, int64_t n_edges, const int64_t *perm, int64_t perm_offset,
+                   int64_t batch, int32_t n_negs, const int64_t *train_indptr, const int32_t *train_indices, int32_t n_items,
+                   uint64_t seed, uint64_t stream_offset, int64_t *out_u, int64_t *out_p, int64_t *out_n, int32_t *gave_up,
+                   hgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
