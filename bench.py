@@ -37,7 +37,11 @@ WORKLOADS = {
     "c3": (30_000, 41_000, 1_000_000, 4096, False),
     "c2": (6_040, 3_706, 750_000, 2048, False),
 }
-MODELS = {"hgnn_hd3": "HGNN_HD3 local encoder (EquivSetConv + HGCNConv), 2 layers", "lightgcn": "LightGCN, 3 layers"}
+MODELS = {"hgnn_hd3": "HGNN_HD3 local encoder (EquivSetConv + HGCNConv), 2 layers", "lightgcn": "LightGCN, 3 layers",
+          "hccf": "HCCF, 2 layers, 128 learned hyperedges, edge keep 0.8, contrastLoss on the batch's unique users/items (temp 0.2)"}
+HCCF_CONF = {"lrate": LR if False else 0.001, "lr_decay": 1.0, "max_epoch": 1, "batch_size": 4096, "reg": 0.0, "embedding_size": 64, "hyper_dim": 128,
+             "drop_rate": 0.2, "p": 0.5, "n_layers": 2}
+HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP = 0.2, 0.1, 0.8
 D = 64
 REG = 0.01
 LR = 0.001
@@ -56,6 +60,7 @@ def parse_args():
     ap.add_argument("--model", default="hgnn_hd3", choices=sorted(MODELS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-clocks", action="store_true", help="diagnosis: do not poll nvidia-smi during the timed region")
     return ap.parse_args()
 
 
@@ -100,6 +105,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
+        note = None
+        if not self.lines:  # timed region shorter than one polling period: one query right after it
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout
+                self.lines = [ln.strip() for ln in out.splitlines() if ln.strip()]
+                note = "timed region shorter than the 200 ms polling period: sampled right after it"
+            except (OSError, subprocess.SubprocessError):
+                pass
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -114,8 +128,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def workload_dims(name, n_gpus):
@@ -144,8 +161,12 @@ def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
     csr = O.build_norm_adj(g.train_u, g.train_i, su, si)
     adj = T.coo_from_csr(*csr, (su + si, su + si))
     torch.manual_seed(1234)
-    model = T.HGNNModel(adj, su, si, D, 2) if model_name == "hgnn_hd3" else T.LGCN(adj, su, si, D, 3)
-    model.eval()  # dropout off, like the GPU arm (the reference's loop leaves it off after the first batch)
+    if model_name == "hccf":
+        model = T.HCCF(adj, su, si, D, 128, 2)
+        model.train()
+    else:
+        model = T.HGNNModel(adj, su, si, D, 2) if model_name == "hgnn_hd3" else T.LGCN(adj, su, si, D, 3)
+        model.eval()  # dropout off, like the GPU arm (the reference's loop leaves it off after the first batch)
     opt = torch.optim.Adam(model.parameters(), lr=LR)
     rng = np.random.default_rng(7)
     times = []
@@ -155,7 +176,10 @@ def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
         p = torch.from_numpy(g.train_i[pick])
         n = torch.from_numpy(rng.integers(0, si, sb))
         t0 = time.perf_counter()
-        T.train_step(model, opt, u, p, n, REG, sb)
+        if model_name == "hccf":
+            T.train_step_hccf(model, opt, u, p, n, HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP)
+        else:
+            T.train_step(model, opt, u, p, n, REG, sb)
         if s >= warmup:
             times.append(time.perf_counter() - t0)
     step_s = sum(times) / len(times)
@@ -165,7 +189,7 @@ def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
     sample = "%d x %d x %d interactions (1/%d of the workload), batch %d, %d threads; step time x %d x %d steps/epoch" % (
         su, si, se, div, sb, cores, div, steps_per_epoch)
     return {"epoch_s": epoch_s, "step_ms_sample": step_s * 1e3, "cores": cores, "sample": sample, "div": div,
-            "nnz_per_s": 2 * se * (12 if model_name == "hgnn_hd3" else 6) / step_s}
+            "nnz_per_s": 2 * se * {"hgnn_hd3": 12, "lightgcn": 6, "hccf": 4}[model_name] / step_s}
 
 
 def run_reference(args):
@@ -226,9 +250,16 @@ def run_ours(args):
     torch.manual_seed(1234)
     if args.model == "hgnn_hd3":
         model = encoders.HGNNModel(data, {"hyper_dim": D, "n_layers": 2, "p": 0.3, "drop_rate": 0.2, "batch_size": B}).to(dev)
+    elif args.model == "hccf":
+        if world > 1:
+            raise SystemExit("--model hccf is a single-GPU workload (BASELINE configs[2])")
+        model = encoders.HCCFEncoder(HCCF_CONF, data).to(dev)
     else:
         model = encoders.LGCN_Encoder(data, D, 3).to(dev)
-    model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
+    if args.model == "hccf":
+        model.train()  # HCCF.train calls model.train() every batch (HCCF.py:81): dropout on the learned incidence stays on
+    else:
+        model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
     optimizer = torch.optim.Adam(model.parameters(), lr=LR, fused=True)
 
     # triples: the device sampler (csrc/sampler.cu: shuffled positives + rejection-sampled negatives, the body of
@@ -266,6 +297,8 @@ def run_ours(args):
     def step(tri):
         if world > 1:
             return hdist.train_step(model, optimizer, adj, tri[0], tri[1], tri[2], REG, B)
+        if args.model == "hccf":
+            return trainer.train_step_hccf(model, optimizer, tri[0], tri[1], tri[2], HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP)
         return trainer.train_step(model, optimizer, tri[0], tri[1], tri[2], REG, B)
 
     def timed(kind):
@@ -311,7 +344,8 @@ def run_ours(args):
         return total, losses, launches
 
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if not args.no_clocks:
+        clocks.start()
     if world > 1:
         adj.n_fused = adj.n_collective = 0
     total_ms, losses, launches = timed("device")

@@ -75,6 +75,9 @@ template <int MODE, int D>
 __global__ void __launch_bounds__(SSL_THREADS) ssl_pass_kernel(const float *__restrict__ X, const float *__restrict__ Y, int64_t M,
                                                                float inv_temp, const float *__restrict__ deno,
                                                                const float *__restrict__ coef, float *__restrict__ out) {
+    // gridDim.y blocks share an owner tile: block y takes every gridDim.y-th looped tile and writes its own partial
+    // result (slice y of `out`); the consumers add the slices in order, so the sums stay deterministic.
+    out += (size_t)blockIdx.y * (size_t)M * (MODE == 0 ? 1 : D);
     extern __shared__ float ssl_sm[];
     constexpr int LD = D + 1;
     float *Xs = ssl_sm;               // [64][D + 1] owner rows
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(SSL_THREADS) ssl_pass_kernel(const float *__re
             oscale[i] = j < M ? coef[j] / deno[j] : 0.f;
         }
     }
-    for (int64_t l0 = 0; l0 < M; l0 += SSL_T) {
+    for (int64_t l0 = (int64_t)blockIdx.y * SSL_T; l0 < M; l0 += (int64_t)gridDim.y * SSL_T) {
         __syncthreads();
         for (int e = threadIdx.x; e < SSL_T * D; e += SSL_THREADS) {
             const int r = e / D, d = e % D;
@@ -173,13 +176,15 @@ __global__ void __launch_bounds__(SSL_THREADS) ssl_pass_kernel(const float *__re
 
 // kind 0 (contrastLoss): deno = rowsum + 1e-8, term = log(deno) - pos / T, c = 1
 // kind 1 (InfoNCE):      r = exp(pos / T) / rowsum, term = -log(r + 10e-6), c = r / (r + 10e-6)
-__global__ void __launch_bounds__(1024) ssl_finish_kernel(const float *__restrict__ rowsum, const float *__restrict__ pos, int64_t M,
-                                                          float inv_temp, int kind, float *__restrict__ deno, float *__restrict__ coef,
-                                                          float *__restrict__ loss) {
+__global__ void __launch_bounds__(1024) ssl_finish_kernel(const float *__restrict__ rowsum, int n_split, const float *__restrict__ pos,
+                                                          int64_t M, float inv_temp, int kind, float *__restrict__ deno,
+                                                          float *__restrict__ coef, float *__restrict__ loss) {
     __shared__ double sh[1024];
     double t = 0.0;
     for (int64_t j = threadIdx.x; j < M; j += 1024) {
-        const float rs = rowsum[j], p = pos[j] * inv_temp;
+        float rs = rowsum[j];
+        for (int s = 1; s < n_split; ++s) rs += rowsum[(int64_t)s * M + j];
+        const float p = pos[j] * inv_temp;
         if (kind == 0) {
             const float dn = rs + 1e-8f;
             deno[j] = dn;
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(1024) ssl_finish_kernel(const float *__restric
 
 // dY_j = scale * (G_j - c_j * other_j)  with scale = grad / (M T); then the normalisation backward
 // dx = (dY - y (dY . y)) / ||x|| and the store to the table row (or row j when there is no index).
-__global__ void __launch_bounds__(256) ssl_scatter_kernel(const float *__restrict__ G, const float *__restrict__ self_n,
+__global__ void __launch_bounds__(256) ssl_scatter_kernel(const float *__restrict__ G, int n_split, const float *__restrict__ self_n,
                                                           const float *__restrict__ other_n, const float *__restrict__ coef,
                                                           const float *__restrict__ nrm, int which, const int64_t *__restrict__ nodes,
                                                           int64_t M, int64_t n_rows, int D, float inv_temp, int normalize,
@@ -220,7 +225,12 @@ __global__ void __launch_bounds__(256) ssl_scatter_kernel(const float *__restric
     for (int q = 0; q < 4; ++q) {
         const int d = lane + 32 * q;
         y[q] = d < D ? self_n[j * D + d] : 0.f;
-        g[q] = d < D ? scale * (G[j * D + d] - c * other_n[j * D + d]) : 0.f;
+        float gs = 0.f;
+        if (d < D) {
+            gs = G[j * D + d];
+            for (int s = 1; s < n_split; ++s) gs += G[((int64_t)s * M + j) * D + d];
+        }
+        g[q] = d < D ? scale * (gs - c * other_n[j * D + d]) : 0.f;
         gy += g[q] * y[q];
     }
     gy = group_sum<32>(gy, 0xffffffffu);
@@ -232,6 +242,17 @@ __global__ void __launch_bounds__(256) ssl_scatter_kernel(const float *__restric
     }
 }
 
+constexpr int SSL_MAX_SPLIT = 8;
+
+// slices of the looped dimension: enough blocks for two waves of 148 SMs
+static int ssl_splits(int64_t M) {
+    const int64_t owners = ceil_div(M > 0 ? M : 1, SSL_T);
+    int64_t s = ceil_div(296, owners);
+    if (s > SSL_MAX_SPLIT) s = SSL_MAX_SPLIT;
+    if (s > owners) s = owners;  // never more slices than looped tiles
+    return (int)(s < 1 ? 1 : s);
+}
+
 struct SslWs {
     float *A, *B, *nrm, *pos, *rowsum, *deno, *coef, *G;
     size_t total;
@@ -239,6 +260,7 @@ struct SslWs {
 
 static SslWs ssl_layout(void *base, int64_t M, int D) {
     SslWs w;
+    const size_t S = (size_t)ssl_splits(M);
     size_t o = 0;
     auto take = [&](size_t n) {
         float *p = base ? reinterpret_cast<float *>(static_cast<uint8_t *>(base) + o) : nullptr;
@@ -250,10 +272,10 @@ static SslWs ssl_layout(void *base, int64_t M, int D) {
     w.B = take(m * D);
     w.nrm = take(2 * m);
     w.pos = take(m);
-    w.rowsum = take(m);
+    w.rowsum = take(m * S);
     w.deno = take(m);
     w.coef = take(m);
-    w.G = take(m * D);
+    w.G = take(m * D * S);
     w.total = o;
     return w;
 }
@@ -261,8 +283,8 @@ static SslWs ssl_layout(void *base, int64_t M, int D) {
 template <int MODE>
 static int launch_pass(int D, const float *X, const float *Y, int64_t M, float inv_temp, const float *deno, const float *coef,
                        float *out, cudaStream_t st) {
-    const unsigned grid = (unsigned)ceil_div(M, SSL_T);
-    if (grid == 0) return HGR_OK;
+    const dim3 grid((unsigned)ceil_div(M, SSL_T), (unsigned)ssl_splits(M));
+    if (grid.x == 0) return HGR_OK;
 #define HGR_SSL_LAUNCH(DD)                                                                                                 \
     {                                                                                                                      \
         const size_t smem = (size_t)(2 * SSL_T * (DD + 1) + SSL_T * 65) * sizeof(float);                                   \
@@ -304,7 +326,7 @@ int hgr_ssl_loss_fwd_f32(const float *E1, const float *E2, int64_t n_rows1, int6
         int rc = launch_pass<0>(D, w.A, w.B, M, inv_temp, nullptr, nullptr, w.rowsum, st);
         if (rc) return rc;
     }
-    ssl_finish_kernel<<<1, 1024, 0, st>>>(w.rowsum, w.pos, M, inv_temp, kind, w.deno, w.coef, loss);
+    ssl_finish_kernel<<<1, 1024, 0, st>>>(w.rowsum, ssl_splits(M), w.pos, M, inv_temp, kind, w.deno, w.coef, loss);
     HGR_LAUNCH_OK("ssl_finish_kernel");
     return HGR_OK;
 }
@@ -322,14 +344,14 @@ int hgr_ssl_loss_bwd_f32(int64_t n_rows1, int64_t n_rows2, int32_t D, const int6
     if (dE1) {
         int rc = launch_pass<1>(D, w.A, w.B, M, inv_temp, w.deno, w.coef, w.G, st);
         if (rc) return rc;
-        ssl_scatter_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(w.G, w.A, w.B, w.coef, w.nrm, 0, nodes, M, n_rows1, D, inv_temp,
+        ssl_scatter_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(w.G, ssl_splits(M), w.A, w.B, w.coef, w.nrm, 0, nodes, M, n_rows1, D, inv_temp,
                                                                     normalize, grad_out, dE1);
         HGR_LAUNCH_OK("ssl_scatter_kernel");
     }
     if (dE2) {
         int rc = launch_pass<2>(D, w.B, w.A, M, inv_temp, w.deno, w.coef, w.G, st);
         if (rc) return rc;
-        ssl_scatter_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(w.G, w.B, w.A, w.coef, w.nrm, 1, nodes, M, n_rows2, D, inv_temp,
+        ssl_scatter_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(w.G, ssl_splits(M), w.B, w.A, w.coef, w.nrm, 1, nodes, M, n_rows2, D, inv_temp,
                                                                     normalize, grad_out, dE2);
         HGR_LAUNCH_OK("ssl_scatter_kernel");
     }

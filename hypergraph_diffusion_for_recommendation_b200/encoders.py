@@ -116,13 +116,18 @@ class SpAdjDropEdge(nn.Module):
         if rand is None:
             rand = torch.rand(nnz)
         mask = ((rand + keepRate).floor()).type(torch.bool).to(adj.device, non_blocking=True)
+        # tensor / tensor is a true IEEE division (the scalar overload multiplies by a reciprocal on CUDA),
+        # which keeps the rescaled values bit-identical to the reference's CPU `vals[mask] / keepRate`
+        keep = torch.full((), float(keepRate), dtype=torch.float32, device=adj.device)
+        if adj.symmetric or getattr(adj, "_tperm", None) is not None:
+            # the normalised adjacency: keep its pattern and split plan, zero the dropped values; the transpose the
+            # backward pass needs is the same pattern with permuted values -- no sort, no host round trip per batch
+            vals = torch.where(mask, adj.values / keep, torch.zeros((), dtype=torch.float32, device=adj.device))
+            return adj.with_values(vals, vals[adj.transpose_permutation()])
         rows = torch.repeat_interleave(torch.arange(adj.shape[0], device=adj.device), adj.indptr[1:] - adj.indptr[:-1])
         counts = torch.bincount(rows[mask], minlength=adj.shape[0])
         indptr = torch.zeros(adj.shape[0] + 1, dtype=torch.int64, device=adj.device)
         torch.cumsum(counts, 0, out=indptr[1:])
-        # tensor / tensor is a true IEEE division (the scalar overload multiplies by a reciprocal on CUDA),
-        # which keeps the rescaled values bit-identical to the reference's CPU `vals[mask] / keepRate`
-        keep = torch.full((), float(keepRate), dtype=torch.float32, device=adj.device)
         return DeviceCSR(indptr, adj.indices[mask], adj.values[mask] / keep, adj.shape, chunk_nnz=adj.chunk_nnz)
 
 
@@ -374,7 +379,9 @@ class HCCFEncoder(nn.Module):
             'item_w': nn.Parameter(initializer(torch.empty(self.latent_size, self.n_edges))),
         })
 
-    def forward(self, keep_rate=0.5):
+    def forward(self, keep_rate=0.5, device_rng=False):
+        """``device_rng``: draw each layer's edge-drop mask with ``torch.rand(nnz, device=cuda)`` instead of the reference's
+        CPU ``torch.rand(nnz)`` + upload (HCCF.py:217-226); the default replays the reference's CPU random stream."""
         n_users = self.data.n_users
         embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
         hidden = [embeddings]
@@ -383,7 +390,8 @@ class HCCFEncoder(nn.Module):
         hyper_uu = self.embedding_dict['user_emb'] @ self.embedding_dict['user_w']
         hyper_ii = self.embedding_dict['item_emb'] @ self.embedding_dict['item_w']
         for i in range(self.n_layers):
-            gcn_emb = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate), hidden[-1])
+            rand = torch.rand(self.sparse_norm_adj._nnz(), device=self.sparse_norm_adj.device) if device_rng and keep_rate != 1.0 else None
+            gcn_emb = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate, rand), hidden[-1])
             hyper_uemb = self.hgnnlayer(self.drop_out(hyper_uu), hidden[-1][:n_users])
             hyper_iemb = self.hgnnlayer(self.drop_out(hyper_ii), hidden[-1][n_users:])
             gcn_hidden += [gcn_emb]

@@ -89,6 +89,47 @@ class DeviceCSR:
             self._t._t = self
         return self._t
 
+    # ---- same sparsity pattern, other values (edge dropout) ---------------------------------------
+    def transpose_permutation(self) -> torch.Tensor:
+        """For a structurally symmetric matrix: ``tperm[p]`` = position of entry (c, r) for the p-th entry (r, c).
+        Computed once (one sort-free ``searchsorted`` over the canonical keys) and cached."""
+        tp = getattr(self, "_tperm", None)
+        if tp is None:
+            n = self.shape[1]
+            rows = torch.repeat_interleave(torch.arange(self.shape[0], device=self.device, dtype=torch.int64),
+                                           self.indptr[1:] - self.indptr[:-1])
+            cols = self.indices.to(torch.int64)
+            tp = torch.searchsorted(rows * n + cols, cols * n + rows)
+            if self.shape[0] != self.shape[1] or not bool((self.indices[tp.clamp(max=max(cols.numel() - 1, 0))] == rows.to(torch.int32)).all()):
+                raise ValueError("transpose_permutation needs a structurally symmetric matrix with sorted columns")
+            self._tperm = tp
+        return tp
+
+    def with_values(self, values: torch.Tensor, t_values: torch.Tensor | None = None) -> "DeviceCSR":
+        """A matrix with THIS sparsity pattern (and split plan) and other values; ``t_values`` are the values of its
+        transpose in this same pattern (structurally symmetric matrices: ``values[transpose_permutation()]``).
+        No host work, no synchronisation: explicit zeros stand in for dropped entries, which leaves every sum
+        bit-identical to the compacted matrix (fma(0, x, acc) == acc)."""
+        import copy
+
+        out = copy.copy(self)
+        out.values = values.contiguous()
+        out.symmetric = False
+        d = _lib.CsrDesc.from_buffer_copy(self.desc)
+        d.values = out.values.data_ptr()
+        out.desc = d
+        out._tperm = getattr(self, "_tperm", None)
+        out._t = None
+        if t_values is not None:
+            t = copy.copy(self)
+            t.values = t_values.contiguous()
+            t.symmetric = False
+            td = _lib.CsrDesc.from_buffer_copy(self.desc)
+            td.values = t.values.data_ptr()
+            t.desc = td
+            t._t, out._t = out, t
+        return out
+
     def to(self, *a, **k):  # `.to(device)` / `.cuda()` on an already-resident handle are no-ops
         return self
 
@@ -123,8 +164,17 @@ class DeviceCSR:
             self._ws[d] = ws
         return ws
 
-    def to_host(self):
-        return self.indptr.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy()
+    def to_host(self, drop_zeros: bool = False):
+        """``(indptr, indices, values)`` as numpy arrays; ``drop_zeros`` removes the explicit zeros an edge-dropped
+        matrix carries (``with_values``), giving the compacted CSR the reference builds."""
+        ip, ix, dv = self.indptr.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy()
+        if drop_zeros:
+            keep = dv != 0
+            rows = np.repeat(np.arange(ip.size - 1), np.diff(ip))[keep]
+            ip = np.zeros_like(ip)
+            np.cumsum(np.bincount(rows, minlength=ip.size - 1), out=ip[1:])
+            ix, dv = ix[keep], dv[keep]
+        return ip, ix, dv
 
 
 def transpose_csr(a: DeviceCSR) -> DeviceCSR:

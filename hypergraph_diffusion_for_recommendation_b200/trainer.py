@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from .loss_torch import bpr_l2_from_tables
+from .loss_torch import bpr_l2_from_tables, contrastLoss
 
 
 def train_step(model, optimizer, user_idx, pos_idx, neg_idx, reg: float, batch_size: int, forward=None):
@@ -21,3 +21,23 @@ def train_step(model, optimizer, user_idx, pos_idx, neg_idx, reg: float, batch_s
     batch_loss.backward()
     optimizer.step()
     return torch.stack([rec_loss.detach(), reg_loss.detach()])
+
+
+def train_step_hccf(model, optimizer, user_idx, pos_idx, neg_idx, temp: float, ss_rate: float, keep_rate: float, device_rng: bool = True):
+    """Per-batch body of ``HCCF.train`` (model/graph/HCCF.py:79-95) with ``calcLosses`` (:59-68): edge-dropped GCN +
+    learned-hyperedge propagation, BPR, and per layer ``contrastLoss`` between the detached GCN view and the hypergraph
+    view for users and items.  SSL nodes = the batch's unique user / positive-item ids (see oracle/torch_path.py).
+    ``device_rng``: draw the edge-drop mask on the GPU instead of the reference's CPU ``torch.rand(nnz)``."""
+    n_users = model.data.n_users
+    user_emb, item_emb, gcn_l, hyp_l = model(keep_rate=keep_rate, device_rng=device_rng)
+    rec_loss, _ = bpr_l2_from_tables(user_emb, item_emb, user_idx, pos_idx, neg_idx, 0.0, 1.0)
+    un, pn = torch.unique(user_idx), torch.unique(pos_idx)
+    ssl = 0
+    for g, h in zip(gcn_l, hyp_l):
+        g = g.detach()
+        ssl = ssl + contrastLoss(g[:n_users], h[:n_users], un, temp) + contrastLoss(g[n_users:], h[n_users:], pn, temp)
+    ssl = ssl * ss_rate
+    optimizer.zero_grad(set_to_none=True)
+    (rec_loss + ssl).backward()
+    optimizer.step()
+    return torch.stack([rec_loss.detach(), ssl.detach()])

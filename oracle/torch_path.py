@@ -131,6 +131,76 @@ class HGNNModel(nn.Module):
         return self.hgnn_layer_local(ego)
 
 
+def contrast_loss(embeds1, embeds2, nodes, temp):
+    """util/loss_torch.py:103-110."""
+    embeds1 = F.normalize(embeds1 + 1e-8, p=2)
+    embeds2 = F.normalize(embeds2 + 1e-8, p=2)
+    pck1, pck2 = embeds1[nodes], embeds2[nodes]
+    nume = torch.exp(torch.sum(pck1 * pck2, dim=-1) / temp)
+    deno = torch.exp(pck1 @ pck2.T / temp).sum(-1) + 1e-8
+    return -torch.log(nume / deno).mean()
+
+
+class HCCF(nn.Module):
+    """``HCCFEncoder`` (model/graph/HCCF.py:136-226): per layer an edge-dropped GCN propagation plus the learned dense
+    hyperedge two-stage on users and items; sum readout; returns the per-layer GCN / hypergraph tables for the SSL loss."""
+
+    def __init__(self, adj, n_users, n_items, width, n_edges, n_layers, drop_rate=0.2):
+        super().__init__()
+        self.adj, self.n_users, self.n_layers = adj, n_users, n_layers
+        init = nn.init.xavier_uniform_
+        self.embedding_dict = nn.ParameterDict({
+            'user_emb': nn.Parameter(init(torch.empty(n_users, width))), 'item_emb': nn.Parameter(init(torch.empty(n_items, width))),
+            'user_w': nn.Parameter(init(torch.empty(width, n_edges))), 'item_w': nn.Parameter(init(torch.empty(width, n_edges)))})
+        self.drop_out = nn.Dropout(drop_rate)
+
+    def drop_edges(self, keep_rate):
+        if keep_rate == 1.0:
+            return self.adj
+        adj = self.adj.coalesce()
+        vals, idxs = adj.values(), adj.indices()
+        mask = ((torch.rand(vals.size()) + keep_rate).floor()).type(torch.bool)  # HCCF.py:217-226
+        return torch.sparse_coo_tensor(idxs[:, mask], vals[mask] / keep_rate, adj.shape)
+
+    def forward(self, keep_rate=0.5):
+        n_users = self.n_users
+        embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
+        hidden, gcn_hidden, hgnn_hidden = [embeddings], [], []
+        hyper_uu = self.embedding_dict['user_emb'] @ self.embedding_dict['user_w']
+        hyper_ii = self.embedding_dict['item_emb'] @ self.embedding_dict['item_w']
+        for _ in range(self.n_layers):
+            gcn_emb = torch.sparse.mm(self.drop_edges(keep_rate), hidden[-1])
+            hu, hi = self.drop_out(hyper_uu), self.drop_out(hyper_ii)
+            hyper_uemb = torch.mm(hu, torch.mm(hu.T, hidden[-1][:n_users]))
+            hyper_iemb = torch.mm(hi, torch.mm(hi.T, hidden[-1][n_users:]))
+            gcn_hidden += [gcn_emb]
+            hgnn_hidden += [torch.cat([hyper_uemb, hyper_iemb], 0)]
+            hidden += [gcn_emb + hgnn_hidden[-1]]
+        embeddings = sum(hidden)
+        return embeddings[:n_users], embeddings[n_users:], gcn_hidden, hgnn_hidden
+
+
+def train_step_hccf(model, optimizer, u_idx, p_idx, n_idx, temp, ss_rate, keep_rate):
+    """model/graph/HCCF.py:79-95 with calcLosses (:59-68).  The SSL nodes are the batch's unique user / positive-item ids
+    (the shipped code passes the gathered EMBEDDINGS to torch.unique(...long()), which collapses the node set to {0};
+    bench.py times the intended computation on both arms and says so in its config)."""
+    n_users = model.n_users
+    user_emb, item_emb, gcn_l, hyp_l = model(keep_rate=keep_rate)
+    rec_loss = bpr_loss(user_emb[u_idx], item_emb[p_idx], item_emb[n_idx])
+    un, pn = torch.unique(u_idx), torch.unique(p_idx)
+    ssl = 0
+    for g, h in zip(gcn_l, hyp_l):
+        g = g.detach()
+        ssl = ssl + contrast_loss(g[:n_users], h[:n_users], un, temp) + contrast_loss(g[n_users:], h[n_users:], pn, temp)
+    ssl = ssl * ss_rate
+    loss = rec_loss + ssl
+    vals = (loss.item(), rec_loss.item(), float(ssl))
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return vals
+
+
 def train_step(model, optimizer, u_idx, p_idx, n_idx, reg, batch_size):
     """model/graph/LightGCN.py:49-66 (same body in HGNN_HD3.py:138-160)."""
     user_all, item_all = model()

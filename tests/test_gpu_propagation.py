@@ -161,7 +161,8 @@ def test_hgconv_forward_backward(hgr, golden, adj):
 
 def test_hgconv_asymmetric_after_edge_drop(hgr, golden, adj):
     dropped = hgr.enc.SpAdjDropEdge()(adj, float(golden["drop_keep"]), rand=torch.from_numpy(golden["drop_rand"]))
-    ip, ix, dv = dropped.to_host()
+    # the dropped matrix keeps the pattern of the adjacency with zeroed values; compacted, it is the reference's matrix
+    ip, ix, dv = dropped.to_host(drop_zeros=True)
     rows = np.repeat(np.arange(ip.size - 1), np.diff(ip))
     assert np.array_equal(np.stack([rows, ix]), golden["drop_indices"])
     assert np.array_equal(bits(dv), bits(golden["drop_values"]))
@@ -172,7 +173,13 @@ def test_hgconv_asymmetric_after_edge_drop(hgr, golden, adj):
     # transpose handle: (A^T)^T round trip and A^T x against the oracle
     tip, tix, tdv = O.csr_transpose(ip.astype(np.int64), ix.astype(np.int64), dv, dropped.shape[1])
     t = dropped.t()
-    assert np.array_equal(t.to_host()[0], tip) and np.array_equal(t.to_host()[1], tix) and np.array_equal(bits(t.to_host()[2]), bits(tdv))
+    th = t.to_host(drop_zeros=True)
+    assert np.array_equal(th[0], tip) and np.array_equal(th[1], tix) and np.array_equal(bits(th[2]), bits(tdv))
+    assert t.t() is dropped
+    # a matrix that is not structurally symmetric still takes the compacting path
+    rect = hgr.graph.DeviceCSR.from_host(ip, ix, dv, dropped.shape)
+    d2 = hgr.enc.SpAdjDropEdge()(rect, 0.5, rand=torch.from_numpy(np.random.default_rng(0).random(ix.size).astype(np.float32)))
+    assert d2._nnz() < rect._nnz() and np.array_equal(bits(hgr.ops.spmm_raw(d2.t().t(), x)), bits(hgr.ops.spmm_raw(d2, x)))
 
 
 def test_lightgcn_propagate_and_backward(hgr, golden, adj, pl_graph):
