@@ -428,12 +428,25 @@ def build_eval_inputs(u, i, U, I, part, rank, dev):
     key = torch.sort((u[m].to(torch.int64) - u0) * I + i[m].to(torch.int64)).values
     indptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
     torch.cumsum(torch.bincount(torch.div(key, I, rounding_mode="floor"), minlength=n_own), 0, out=indptr[1:])
-    return {"n_own": n_own, "indptr": indptr, "indices": (key % I).to(torch.int32), "n_items": I}
+    # held-out interactions of the same users: fresh draws from the generator's distribution that are not training pairs
+    # (the reference's 75 / 25 split, dataset_util.py:20-37), as CSR for the metric code
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device
+
+    n_draw = max(int(u.numel()) // 3, 1024)
+    tu, ti = powerlaw_interactions_device(U, I, n_draw, dev, seed=4321, cover=False, perm_seed=1234)
+    tm = (tu >= u0) & (tu < u0 + n_own)
+    tkey = torch.unique((tu[tm].to(torch.int64) - u0) * I + ti[tm].to(torch.int64))
+    tkey = tkey[~torch.isin(tkey, key)]
+    tptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.bincount(torch.div(tkey, I, rounding_mode="floor"), minlength=n_own), 0, out=tptr[1:])
+    return {"n_own": n_own, "indptr": indptr, "indices": (key % I).to(torch.int32), "n_items": I,
+            "truth_indptr": tptr.cpu().numpy(), "truth_items": (tkey % I).cpu().numpy()}
 
 
 def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
     """Full-ranking evaluation sharded by user: every rank ranks its own users against the whole item table
     (gathered once), top-EVAL_K with the training items masked.  users/s = users of all ranks / max time."""
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -469,6 +482,15 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             ms, n_users_total = float(tmax[0]), int(t[1])
+        # Recall@20 / NDCG@20 of this rank's users through the reference's metric arithmetic (util/evaluation.py), users
+        # with held-out items only, exactly like GraphRecommender.test iterates data.test_set; outside the timed region
+        has = np.diff(ev["truth_indptr"]) > 0
+        sel = np.nonzero(has)[0]
+        ptr = np.zeros(sel.size + 1, dtype=np.int64)
+        np.cumsum(np.diff(ev["truth_indptr"])[sel], out=ptr[1:])
+        t_m = time.perf_counter()
+        measures = E.ranking_evaluation_ids(ptr, ev["truth_items"], host_ids.numpy()[sel], [EVAL_K]) if sel.size else []
+        measure_s = time.perf_counter() - t_m
         s = stats.tolist()
         flops = 2.0 * D * ev["n_items"] * n_users_total
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -477,7 +499,8 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
                 "mode": "exact", "d2h_bytes": int(host_ids.numel() * 4), "score_tflops": tf,
                 "tensor_frac_of_measured_bf16": tf / (peaks.get("bf16_tflops", 1590.0) * world),
                 "candidates_per_user": s[0] / max(ev["n_own"], 1), "rescored_per_user": s[1] / max(ev["n_own"], 1),
-                "fallback_users": s[2]}
+                "fallback_users": s[2], "metrics_rank0": [m.strip() for m in measures], "metrics_users_rank0": int(sel.size),
+                "metrics_host_s": measure_s}
 
 
 def main():

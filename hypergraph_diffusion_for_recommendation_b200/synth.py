@@ -114,7 +114,7 @@ def reference_dense_ids(train_u: np.ndarray, train_i: np.ndarray) -> tuple[np.nd
 
 
 def powerlaw_interactions_device(n_users: int, n_items: int, n_train: int, device, seed: int = 1234,
-                                 chunk: int = 1 << 27):
+                                 chunk: int = 1 << 27, cover: bool = True, perm_seed: int | None = None):
     """Device generator for shapes where the numpy path is too slow (C5). Returns int32 tensors
     ``(train_u, train_i)`` of unique pairs; the test split is drawn by the caller from the same
     distribution. Sampling is inverse-CDF through ``torch.searchsorted``."""
@@ -129,8 +129,14 @@ def powerlaw_interactions_device(n_users: int, n_items: int, n_train: int, devic
     icdf = torch.cumsum(iw, 0)
     icdf /= icdf[-1].clone()
     del uw, iw
-    uperm = torch.randperm(n_users, device=device, generator=gen)
-    iperm = torch.randperm(n_items, device=device, generator=gen)
+    # popularity ranks -> ids.  ``perm_seed`` = the seed of another call: same popular users / items, fresh draws
+    # (held-out interactions of a graph generated with that seed)
+    pgen = gen
+    if perm_seed is not None:
+        pgen = torch.Generator(device=device)
+        pgen.manual_seed(perm_seed)
+    uperm = torch.randperm(n_users, device=device, generator=pgen)
+    iperm = torch.randperm(n_items, device=device, generator=pgen)
 
     def draw(m):
         ru = torch.rand(m, device=device, dtype=torch.float64, generator=gen)
@@ -141,14 +147,17 @@ def powerlaw_interactions_device(n_users: int, n_items: int, n_train: int, devic
         del ri
         return u * n_items + i
 
-    cu = torch.arange(n_users, device=device, dtype=torch.int64)
-    ri = torch.rand(n_users, device=device, dtype=torch.float64, generator=gen)
-    cov1 = cu * n_items + iperm[torch.searchsorted(icdf, ri).clamp_(max=n_items - 1)]
-    di = torch.arange(n_items, device=device, dtype=torch.int64)
-    ru = torch.rand(n_items, device=device, dtype=torch.float64, generator=gen)
-    cov2 = uperm[torch.searchsorted(ucdf, ru).clamp_(max=n_users - 1)] * n_items + di
-    keys = torch.unique(torch.cat([cov1, cov2]))
-    del cu, ri, di, ru, cov1, cov2
+    if cover:  # one interaction for every user and for every item (training graphs)
+        cu = torch.arange(n_users, device=device, dtype=torch.int64)
+        ri = torch.rand(n_users, device=device, dtype=torch.float64, generator=gen)
+        cov1 = cu * n_items + iperm[torch.searchsorted(icdf, ri).clamp_(max=n_items - 1)]
+        di = torch.arange(n_items, device=device, dtype=torch.int64)
+        ru = torch.rand(n_items, device=device, dtype=torch.float64, generator=gen)
+        cov2 = uperm[torch.searchsorted(ucdf, ru).clamp_(max=n_users - 1)] * n_items + di
+        keys = torch.unique(torch.cat([cov1, cov2]))
+        del cu, ri, di, ru, cov1, cov2
+    else:
+        keys = torch.empty(0, dtype=torch.int64, device=device)
     while keys.numel() < n_train:
         need = n_train - keys.numel()
         m = min(int(need * 1.5) + 4096, chunk * 8)
