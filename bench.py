@@ -489,7 +489,7 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
         ptr = np.zeros(sel.size + 1, dtype=np.int64)
         np.cumsum(np.diff(ev["truth_indptr"])[sel], out=ptr[1:])
         t_m = time.perf_counter()
-        measures = E.ranking_evaluation_ids(ptr, ev["truth_items"], host_ids.numpy()[sel], [EVAL_K]) if sel.size else []
+        measures = E.ranking_evaluation_device(ptr, ev["truth_items"], ids[torch.from_numpy(sel).to(dev)], [EVAL_K]) if sel.size else []
         measure_s = time.perf_counter() - t_m
         s = stats.tolist()
         flops = 2.0 * D * ev["n_items"] * n_users_total
@@ -500,7 +500,7 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
                 "tensor_frac_of_measured_bf16": tf / (peaks.get("bf16_tflops", 1590.0) * world),
                 "candidates_per_user": s[0] / max(ev["n_own"], 1), "rescored_per_user": s[1] / max(ev["n_own"], 1),
                 "fallback_users": s[2], "metrics_rank0": [m.strip() for m in measures], "metrics_users_rank0": int(sel.size),
-                "metrics_host_s": measure_s}
+                "metrics_s": measure_s}
 
 
 def main():

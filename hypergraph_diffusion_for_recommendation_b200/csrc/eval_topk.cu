@@ -984,3 +984,58 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ ranking metrics
+// Per-user pieces of util/evaluation.py (Metric.hits :9-15, Metric.NDCG :85-97) from the [n_test, K] id matrix:
+//   hits[r][q] = | set(truth of r) ∩ set(ids[r][:N_q]) |      (a duplicated recommendation counts once)
+//   dcg[r][q]  = sum over positions p < N_q with ids[r][p] in truth of disc[p]   (duplicates count every time, in
+//                position order, in double: the same additions as the python loop)
+// disc[p] = 1.0 / math.log(p + 2, 2) is passed in by the host so that the doubles are python's own.
+// One thread per user; truth rows sorted ascending (binary search); the sums over users stay on the host, in the
+// reference's order, so the rounded metric strings are identical.
+namespace hgr {
+__global__ void __launch_bounds__(128) rank_metrics_kernel(const int32_t *__restrict__ ids, int n_test, int K,
+                                                           const int64_t *__restrict__ truth_indptr,
+                                                           const int32_t *__restrict__ truth_items, const int32_t *__restrict__ top_n,
+                                                           int n_top, const double *__restrict__ disc, int32_t *__restrict__ hits,
+                                                           double *__restrict__ dcg) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_test) return;
+    const int64_t t0 = truth_indptr[r], t1 = truth_indptr[r + 1];
+    const int32_t *row = ids + (int64_t)r * K;
+    int h = 0;
+    double d = 0.0;
+    int q = 0;
+    for (int p = 0; p < K && q < n_top; ++p) {
+        const int id = row[p];
+        if (id >= 0 && is_train_item(truth_items, t0, t1, id)) {
+            d += disc[p];
+            bool first = true;
+            for (int e = 0; e < p; ++e) first = first && row[e] != id;
+            h += first;
+        }
+        while (q < n_top && p + 1 == top_n[q]) {  // top_n ascending
+            hits[(int64_t)r * n_top + q] = h;
+            dcg[(int64_t)r * n_top + q] = d;
+            ++q;
+        }
+    }
+    for (; q < n_top; ++q) {  // N_q > K: the list is shorter than N
+        hits[(int64_t)r * n_top + q] = h;
+        dcg[(int64_t)r * n_top + q] = d;
+    }
+}
+}  // namespace hgr
+
+extern "C" int hgr_rank_metrics(const int32_t *ids, int64_t n_test, int32_t K, const int64_t *truth_indptr, const int32_t *truth_items,
+                                const int32_t *top_n, int32_t n_top, const double *disc, int32_t *hits, double *dcg,
+                                hgr_stream_t stream) {
+    using namespace hgr;
+    HGR_REQUIRE(n_test >= 0 && K >= 1 && n_top >= 1 && n_top <= 16, "bad n_test / K / n_top");
+    if (n_test == 0) return HGR_OK;
+    HGR_REQUIRE(ids && truth_indptr && top_n && disc && hits && dcg, "NULL argument");
+    rank_metrics_kernel<<<(unsigned)ceil_div(n_test, 128), 128, 0, (cudaStream_t)stream>>>(ids, (int)n_test, K, truth_indptr, truth_items,
+                                                                                         top_n, n_top, disc, hits, dcg);
+    HGR_LAUNCH_OK("rank_metrics_kernel");
+    return HGR_OK;
+}

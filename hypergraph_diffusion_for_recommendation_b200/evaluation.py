@@ -180,10 +180,11 @@ def ranking_evaluation_ids(truth_indptr, truth_items, rec_ids, N):
     disc = np.array([1.0 / math.log(n + 2, 2) for n in range(k)], dtype=np.float64)
     measure = []
     for n in N:
-        h = hit[:, :n]
+        m = min(n, k)  # a list shorter than N is used whole (res[user][:n])
+        h = hit[:, :m]
         # Metric.hits counts a SET intersection: a duplicated recommendation (refquirk) counts once
         first = np.ones_like(h)
-        for j in range(1, n):
+        for j in range(1, m):
             first[:, j] = ~(rec_ids[:, :j] == rec_ids[:, j:j + 1]).any(axis=1)
         hits = (h & first).sum(axis=1)
         hits_l = hits.tolist()
@@ -197,17 +198,66 @@ def ranking_evaluation_ids(truth_indptr, truth_items, rec_ids, N):
         recall = round(sum(recall_list) / len(recall_list), 5)
         # NDCG sums 1/log2(pos + 2) over EVERY hit position (duplicates included), in position order
         dcg = np.zeros(n_users, dtype=np.float64)
-        for j in range(n):
+        for j in range(m):
             dcg = np.where(h[:, j], dcg + disc[j], dcg)
-        idcg_tab = np.zeros(k + 1, dtype=np.float64)
+        idcg_tab = np.zeros(max(k, n) + 1, dtype=np.float64)
         acc = 0
-        for j in range(k):
+        for j in range(max(k, n)):
             acc += 1.0 / math.log(j + 2, 2)
             idcg_tab[j + 1] = acc
         idcg = idcg_tab[np.minimum(n_truth, n)]
         sum_ndcg = 0
         for x in (dcg / idcg).tolist():
             sum_ndcg += x
+        ndcg = round(sum_ndcg / n_users, 5)
+        measure.append('Top ' + str(n) + '\n')
+        measure += ['Hit Ratio:' + str(hr) + '\n', 'Precision:' + str(prec) + '\n', 'Recall:' + str(recall) + '\n',
+                    'NDCG:' + str(ndcg) + '\n']
+    return measure
+
+
+def ranking_evaluation_device(truth_indptr, truth_items, rec_ids: torch.Tensor, N):
+    """``ranking_evaluation_ids`` with the per-user work (set intersections, DCG) on the device (``hgr_rank_metrics``):
+    ``rec_ids`` is the device id matrix of ``fullrank_topk``; only ``[n_test, len(N)]`` hits / DCG values come back.  The
+    sums over users run on the host in the reference's order, so the strings are identical to ``ranking_evaluation``."""
+    dev = rec_ids.device
+    rec_ids = rec_ids.to(torch.int32).contiguous()
+    n_users, k = rec_ids.shape
+    tp = torch.as_tensor(np.asarray(truth_indptr, dtype=np.int64))
+    ti = torch.as_tensor(np.asarray(truth_items, dtype=np.int64))
+    n_truth = (tp[1:] - tp[:-1])
+    # sort every truth row ascending (row id is the major key)
+    rows = torch.repeat_interleave(torch.arange(n_users, dtype=torch.int64), n_truth)
+    order = torch.argsort(rows * (1 << 32) + (ti + 1))
+    ti_sorted = ti[order].to(torch.int32).to(dev)
+    tp_dev = tp.to(dev)
+    top = sorted(int(n) for n in N)
+    top_dev = torch.tensor(top, dtype=torch.int32, device=dev)
+    disc = torch.tensor([1.0 / math.log(p + 2, 2) for p in range(k)], dtype=torch.float64, device=dev)
+    hits = torch.empty((n_users, len(top)), dtype=torch.int32, device=dev)
+    dcg = torch.empty((n_users, len(top)), dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().hgr_rank_metrics(rec_ids.data_ptr(), n_users, k, tp_dev.data_ptr(), ti_sorted.data_ptr(), top_dev.data_ptr(),
+                                           len(top), disc.data_ptr(), hits.data_ptr(), dcg.data_ptr(), _lib.stream_ptr()))
+    hits_h, dcg_h = hits.cpu().numpy(), dcg.cpu().numpy()
+    n_truth_l = n_truth.tolist()
+    total_num = int(n_truth.sum())
+    idcg_tab = [0.0]
+    for j in range(max(max(top), k)):
+        idcg_tab.append(idcg_tab[-1] + 1.0 / math.log(j + 2, 2))
+    measure = []
+    for n in N:
+        q = top.index(int(n))
+        hits_l = hits_h[:, q].tolist()
+        hit_num = 0
+        for x in hits_l:
+            hit_num += x
+        hr = round(hit_num / total_num, 5)
+        prec = round(sum(hits_l) / (n_users * n), 5)
+        recall_list = [a / b for a, b in zip(hits_l, n_truth_l)]
+        recall = round(sum(recall_list) / len(recall_list), 5)
+        sum_ndcg = 0
+        for d, m in zip(dcg_h[:, q].tolist(), n_truth_l):
+            sum_ndcg += d / idcg_tab[min(m, n)]
         ndcg = round(sum_ndcg / n_users, 5)
         measure.append('Top ' + str(n) + '\n')
         measure += ['Hit Ratio:' + str(hr) + '\n', 'Precision:' + str(prec) + '\n', 'Recall:' + str(recall) + '\n',

@@ -256,6 +256,15 @@ int hgr_bpr_sample(const int32_t *edge_u, const int32_t *edge_i, int64_t n_edges
                    uint64_t seed, uint64_t stream_offset, int64_t *out_u, int64_t *out_p, int64_t *out_n, int32_t *gave_up,
                    hgr_stream_t stream);
 
+/* Per-user pieces of the ranking metrics (util/evaluation.py: Metric.hits :9-15, Metric.NDCG :85-97) from the id matrix of
+ * hgr_fullrank_topk_f32: for every test user r and every N = top_n[q] (ascending, q < n_top <= 16)
+ *   hits[r][q] = | set(truth items of r) & set(ids[r][:N]) |,   dcg[r][q] = sum of disc[p] over hit positions p < N
+ * (double, position order; disc[p] = 1 / math.log(p + 2, 2) supplied by the host).  truth rows (truth_indptr int64
+ * [n_test + 1], truth_items int32) must be sorted ascending; -1 entries (items unseen in training) never match.
+ * The sums over users are left to the host so that the rounded strings equal the reference's. */
+int hgr_rank_metrics(const int32_t *ids, int64_t n_test, int32_t K, const int64_t *truth_indptr, const int32_t *truth_items,
+                     const int32_t *top_n, int32_t n_top, const double *disc, int32_t *hits, double *dcg, hgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,8 @@ def test_golden_reference_rec_lists_and_metric_strings(E, golden, pl_graph):
         items = np.array([item.get(x, -1) for r in users_raw for x in truth[int(r)]], dtype=np.int64)
         strings = E.ranking_evaluation_ids(ptr, items, ids, [10, 20])
         assert strings == [str(s) for s in golden["eval_measures"]], engine
+        # the same strings with the per-user work on the device (hgr_rank_metrics)
+        assert E.ranking_evaluation_device(ptr, items, cuda(ids.astype(np.int32)), [10, 20]) == strings
     check_exact(E, golden["eval_user_emb"], golden["eval_item_emb"], test_users, tip, tix.astype(np.int32), 20)
 
 
@@ -210,3 +212,23 @@ def test_engines_agree_at_gowalla_scale(E):
     users = ev.test_users.cpu().numpy()
     for r in range(0, users.size, 997):
         assert not np.isin(ids[r], idx[ptr[users[r]]:ptr[users[r] + 1]]).any()
+
+
+def test_device_metric_reducer_matches_host_and_oracle_with_duplicates_and_unknown_items(E):
+    rng = np.random.default_rng(21)
+    n_users, n_items, k = 4000, 3000, 40
+    truth = [rng.choice(n_items, rng.integers(1, 60), replace=False).astype(np.int64) for _ in range(n_users)]
+    for t in truth[::7]:
+        t[0] = -1                                    # an item never seen in training: counts in |truth|, never hit
+    rec = rng.integers(0, n_items, (n_users, k))
+    rec[:, 9] = rec[:, 3]                            # duplicated recommendations (the reference's quirk)
+    rec[::5, 0] = [t[-1] if t[-1] >= 0 else 0 for t in truth[::5]]  # guaranteed hits (never the -1 placeholder)
+    ptr = np.zeros(n_users + 1, np.int64)
+    np.cumsum([len(t) for t in truth], out=ptr[1:])
+    items = np.concatenate(truth)
+    for top in ([10, 20, 40], [20], [5, 40, 50]):
+        host = E.ranking_evaluation_ids(ptr, items, rec, top)
+        assert E.ranking_evaluation_device(ptr, items, cuda(rec.astype(np.int32)), top) == host
+    assert host[:1] == ["Top 5\n"]
+    want = O.ranking_evaluation([list(t) for t in truth], rec, [10, 20, 40])
+    assert E.ranking_evaluation_device(ptr, items, cuda(rec.astype(np.int32)), [10, 20, 40]) == want
