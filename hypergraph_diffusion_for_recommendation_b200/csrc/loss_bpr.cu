@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_bwd_kernel(const float4 *
                                                                   int64_t n_items, const float *__restrict__ saved_x,
                                                                   const float *__restrict__ norms, const float *__restrict__ grad_out,
                                                                   float reg, float batch_size_div, float *__restrict__ d_user,
-                                                                  float *__restrict__ d_item) {
+                                                                  float *__restrict__ d_item, int64_t row_lo, int64_t row_hi) {
+    // [row_lo, row_hi): only gradient rows inside the window are produced, at d[row - row_lo] (sharded training: a rank
+    // owns a window of the gathered table); the default window is the whole table.
     constexpr int GPB = kLossThreads / LPR;
     const int gl = threadIdx.x % LPR, g = threadIdx.x / LPR;
     const float g_rec = grad_out[0], g_reg = grad_out[1];
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_bwd_kernel(const float4 *
     for (int64_t b = (int64_t)blockIdx.x * GPB + g; b < batch; b += (int64_t)gridDim.x * GPB) {
         const int64_t iu = u[b], ip = p[b], in = n[b];
         if (iu < 0 || iu >= n_users || ip < 0 || ip >= n_items || in < 0 || in >= n_items) continue;
+        const bool wu = iu >= row_lo && iu < row_hi, wp = ip >= row_lo && ip < row_hi, wn = in >= row_lo && in < row_hi;
+        if (!(wu || wp || wn)) continue;
         const float4 a = __ldg(user_tab + iu * LPR + gl);
         const float4 q = __ldg(item_tab + ip * LPR + gl);
         const float4 r = __ldg(item_tab + in * LPR + gl);
@@ -119,9 +123,9 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_bwd_kernel(const float4 *
         du.z = gx * (q.z - r.z) + cu * a.z; du.w = gx * (q.w - r.w) + cu * a.w;
         dp.x = gx * a.x + cp * q.x; dp.y = gx * a.y + cp * q.y; dp.z = gx * a.z + cp * q.z; dp.w = gx * a.w + cp * q.w;
         dn.x = -gx * a.x + cn * r.x; dn.y = -gx * a.y + cn * r.y; dn.z = -gx * a.z + cn * r.z; dn.w = -gx * a.w + cn * r.w;
-        red_add_f4(d_user + (iu * LPR + gl) * 4, du);
-        red_add_f4(d_item + (ip * LPR + gl) * 4, dp);
-        red_add_f4(d_item + (in * LPR + gl) * 4, dn);
+        if (wu) red_add_f4(d_user + ((iu - row_lo) * LPR + gl) * 4, du);
+        if (wp) red_add_f4(d_item + ((ip - row_lo) * LPR + gl) * 4, dp);
+        if (wn) red_add_f4(d_item + ((in - row_lo) * LPR + gl) * 4, dn);
     }
 }
 
@@ -173,9 +177,10 @@ int hgr_bpr_l2_fwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
     return HGR_OK;
 }
 
-int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
-                       const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div,
-                       const void *saved, const float *grad_out, float *d_user_tab, float *d_item_tab, hgr_stream_t stream) {
+static int bpr_bwd_impl(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D, const int64_t *u,
+                        const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div, const void *saved,
+                        const float *grad_out, float *d_user_tab, float *d_item_tab, int64_t row_lo, int64_t row_hi,
+                        hgr_stream_t stream) {
     using namespace hgr;
     HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
     HGR_REQUIRE(batch >= 0, "negative batch");
@@ -187,12 +192,29 @@ int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
     cudaStream_t st = (cudaStream_t)stream;
     const float4 *ut = reinterpret_cast<const float4 *>(user_tab), *it = reinterpret_cast<const float4 *>(item_tab);
     switch (D) {
-        case 32: bpr_l2_bwd_kernel<8><<<loss_blocks(batch, kLossThreads / 8), kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, norms, grad_out, reg, batch_size_div, d_user_tab, d_item_tab); break;
-        case 64: bpr_l2_bwd_kernel<16><<<loss_blocks(batch, kLossThreads / 16), kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, norms, grad_out, reg, batch_size_div, d_user_tab, d_item_tab); break;
-        default: bpr_l2_bwd_kernel<32><<<loss_blocks(batch, kLossThreads / 32), kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, norms, grad_out, reg, batch_size_div, d_user_tab, d_item_tab); break;
+        case 32: bpr_l2_bwd_kernel<8><<<loss_blocks(batch, kLossThreads / 8), kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, norms, grad_out, reg, batch_size_div, d_user_tab, d_item_tab, row_lo, row_hi); break;
+        case 64: bpr_l2_bwd_kernel<16><<<loss_blocks(batch, kLossThreads / 16), kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, norms, grad_out, reg, batch_size_div, d_user_tab, d_item_tab, row_lo, row_hi); break;
+        default: bpr_l2_bwd_kernel<32><<<loss_blocks(batch, kLossThreads / 32), kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, norms, grad_out, reg, batch_size_div, d_user_tab, d_item_tab, row_lo, row_hi); break;
     }
     HGR_LAUNCH_OK("bpr_l2_bwd_kernel");
     return HGR_OK;
+}
+
+int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
+                       const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div,
+                       const void *saved, const float *grad_out, float *d_user_tab, float *d_item_tab, hgr_stream_t stream) {
+    const int64_t hi = n_users > n_items ? n_users : n_items;
+    return bpr_bwd_impl(user_tab, item_tab, n_users, n_items, D, u, p, n, batch, reg, batch_size_div, saved, grad_out, d_user_tab,
+                        d_item_tab, 0, hi, stream);
+}
+
+int hgr_bpr_l2_bwd_window_f32(const float *table, int64_t n_rows, int32_t D, const int64_t *u, const int64_t *p, const int64_t *n,
+                              int64_t batch, float reg, float batch_size_div, const void *saved, const float *grad_out,
+                              int64_t row_lo, int64_t row_hi, float *d_rows, hgr_stream_t stream) {
+    HGR_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= n_rows, "window [%lld, %lld) outside the table", (long long)row_lo,
+                (long long)row_hi);
+    return bpr_bwd_impl(table, table, n_rows, n_rows, D, u, p, n, batch, reg, batch_size_div, saved, grad_out, d_rows, d_rows, row_lo,
+                        row_hi, stream);
 }
 
 }  // extern "C"

@@ -283,7 +283,7 @@ class DistGraph:
         return _AllGatherRows.apply(own, self, grad_mode)
 
 
-def _lightgcn_rows(g: DistGraph, e0, n_layers, sum_readout):
+def _lightgcn_rows(g: DistGraph, e0, n_layers, sum_readout, publish_last=False):
     if n_layers == 0:
         return e0.clone()
     layers = [e0]
@@ -298,7 +298,11 @@ def _lightgcn_rows(g: DistGraph, e0, n_layers, sum_readout):
                 full = g.all_gather(cur)
             layers.append(cur)
         else:
-            cur = g.k.spmm(g.block, full, dict(addends=layers, scale=1.0 if sum_readout else 1.0 / (n_layers + 1)))
+            ep = dict(addends=layers, scale=1.0 if sum_readout else 1.0 / (n_layers + 1))
+            if publish_last and g.fused and g.pool(e0.shape[1]) is not None:
+                _, cur = g.spmm_published(full, ep, want_local=True)  # the loss (or the evaluation) gathers these rows next
+            else:
+                cur = g.k.spmm(g.block, full, ep)
     return cur
 
 
@@ -306,7 +310,7 @@ class _DistLightGCN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, e0, g, n_layers, sum_readout):
         ctx.g, ctx.n_layers, ctx.sum_readout = g, n_layers, sum_readout
-        return _lightgcn_rows(g, e0.contiguous(), n_layers, sum_readout)
+        return _lightgcn_rows(g, e0.contiguous(), n_layers, sum_readout, publish_last=True)
 
     @staticmethod
     def backward(ctx, dout):
@@ -389,17 +393,34 @@ def sync_replicated_grads(model, owned_names=("embedding_dict.user_emb", "embedd
         off += g.numel()
 
 
+def _unsplit(out_u: torch.Tensor, out_i: torch.Tensor) -> torch.Tensor:
+    """The encoders return ``(rows[:n_users], rows[n_users:])``: when both are views covering one table, use that table
+    itself (so a gathered copy published by the kernel that produced it can be found) instead of concatenating them."""
+    base = out_u._base
+    if (base is not None and base is out_i._base and base.dim() == 2 and base.is_contiguous() and out_u.data_ptr() == base.data_ptr()
+            and out_u.shape[0] + out_i.shape[0] == base.shape[0] and out_u.shape[1] == base.shape[1]
+            and out_i.data_ptr() == base.data_ptr() + out_u.numel() * base.element_size()):
+        return base
+    return torch.cat([out_u, out_i], 0)
+
+
 def train_step(model, optimizer, g: DistGraph, user_idx, pos_idx, neg_idx, reg: float, batch_size: int, loss_fn=None):
     """One sharded step of the reference's training loop (model/graph/LightGCN.py:49-66): propagate the owned
     rows, gather the final tables, fused BPR + L2 on the whole batch, backward, summed replicated gradients,
     optimiser step on the owned rows.  ``user_idx / pos_idx / neg_idx`` are GLOBAL dense ids."""
-    if loss_fn is None:
-        from .loss_torch import bpr_l2_from_tables as loss_fn
     out_u, out_i = model()[:2]
-    full = g.gather_tables(torch.cat([out_u, out_i], 0))
+    own = _unsplit(out_u, out_i)
     part = g.part
-    rec_loss, reg_loss = loss_fn(full, full, part.perm_user(user_idx), part.perm_item(pos_idx), part.perm_item(neg_idx), reg,
-                                 batch_size)
+    pu, pp, pn = part.perm_user(user_idx), part.perm_item(pos_idx), part.perm_item(neg_idx)
+    if loss_fn is None:
+        # product path: the gathered table comes from the last propagation's epilogue when it published it; the backward
+        # produces only this rank's gradient rows
+        from .loss_torch import bpr_l2_sharded
+
+        rec_loss, reg_loss = bpr_l2_sharded(own, g.gathered, g.rank * part.n_loc, pu, pp, pn, reg, batch_size)
+    else:
+        full = g.gather_tables(own)
+        rec_loss, reg_loss = loss_fn(full, full, pu, pp, pn, reg, batch_size)
     optimizer.zero_grad(set_to_none=True)
     (rec_loss + reg_loss).backward()
     if g.world > 1:

@@ -56,6 +56,46 @@ class _BprL2(torch.autograd.Function):
         return du, di, None, None, None, None, None
 
 
+class _BprL2Sharded(torch.autograd.Function):
+    """BPR + L2 over ONE gathered table of which this rank owns rows ``[row_lo, row_hi)``: the forward gathers the table
+    (``gather`` callable: a collective, or the copy a propagation kernel already published), evaluates the loss on the whole
+    batch (identical on every rank), and the backward produces only the owned gradient rows (hgr_bpr_l2_bwd_window_f32)."""
+
+    @staticmethod
+    def forward(ctx, own, gather, row_lo, u, p, n, reg, batch_size):
+        full = gather(own).contiguous()
+        dev = full.device
+        u, p, n = _idx(u, dev), _idx(p, dev), _idx(n, dev)
+        batch = int(u.numel())
+        lib = _lib.lib()
+        saved = torch.empty(int(lib.hgr_bpr_l2_workspace_bytes(batch)), dtype=torch.uint8, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.hgr_bpr_l2_fwd_f32(full.data_ptr(), full.data_ptr(), full.shape[0], full.shape[0], full.shape[1], u.data_ptr(),
+                                          p.data_ptr(), n.data_ptr(), batch, float(reg), float(batch_size), out.data_ptr(),
+                                          saved.data_ptr(), saved.numel(), bad.data_ptr(), _lib.stream_ptr()))
+        ctx.save_for_backward(full, u, p, n, saved)
+        ctx.meta = (int(row_lo), int(own.shape[0]), float(reg), float(batch_size))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        full, u, p, n, saved = ctx.saved_tensors
+        row_lo, n_own, reg, batch_size = ctx.meta
+        d = torch.zeros((n_own, full.shape[1]), dtype=torch.float32, device=full.device)
+        grad = grad.contiguous().to(torch.float32)
+        _lib.check(_lib.lib().hgr_bpr_l2_bwd_window_f32(full.data_ptr(), full.shape[0], full.shape[1], u.data_ptr(), p.data_ptr(),
+                                                        n.data_ptr(), int(u.numel()), reg, batch_size, saved.data_ptr(), grad.data_ptr(),
+                                                        row_lo, row_lo + n_own, d.data_ptr(), _lib.stream_ptr()))
+        return d, None, None, None, None, None, None, None
+
+
+def bpr_l2_sharded(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size):
+    """``(rec_loss, reg_loss)`` for sharded training; ``user_idx / pos_idx / neg_idx`` index the gathered table."""
+    out = _BprL2Sharded.apply(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size)
+    return out[0], out[1]
+
+
 def bpr_l2_from_tables(user_tab, item_tab, user_idx, pos_idx, neg_idx, reg, batch_size):
     """Returns ``(rec_loss, reg_loss)`` as 0-d tensors; ``reg_loss`` already carries ``/ batch_size``."""
     out = _BprL2.apply(user_tab, item_tab, user_idx, pos_idx, neg_idx, reg, batch_size)

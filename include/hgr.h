@@ -191,6 +191,12 @@ int hgr_bpr_l2_bwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
                        const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg,
                        float batch_size_div, const void *saved, const float *grad_out, float *d_user_tab,
                        float *d_item_tab, hgr_stream_t stream);
+/* Sharded training (dist.py): users and items index ONE gathered table of n_rows rows (forward called with
+ * user_tab == item_tab == table) and this rank needs only the gradient rows [row_lo, row_hi) it owns:
+ * d_rows[(row - row_lo), :] (zero-filled by the caller).  Triples that touch no owned row are skipped. */
+int hgr_bpr_l2_bwd_window_f32(const float *table, int64_t n_rows, int32_t D, const int64_t *u, const int64_t *p, const int64_t *n,
+                              int64_t batch, float reg, float batch_size_div, const void *saved, const float *grad_out,
+                              int64_t row_lo, int64_t row_hi, float *d_rows, hgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Full-ranking evaluation: GraphRecommender.test (base/graph_recommender.py:61-92, identical in
