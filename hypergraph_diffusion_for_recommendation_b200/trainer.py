@@ -41,3 +41,40 @@ def train_step_hccf(model, optimizer, user_idx, pos_idx, neg_idx, temp: float, s
     (rec_loss + ssl).backward()
     optimizer.step()
     return torch.stack([rec_loss.detach(), ssl.detach()])
+
+
+class GraphedTrainStep:
+    """``train_step`` captured once into a CUDA graph and replayed: for graphs whose propagation takes tens of microseconds
+    (the L2-resident BASELINE shapes) the step is bound by ~25-60 kernel launches and the Python between them, not by the
+    kernels.  The batch's index tensors are copied into static buffers, the whole forward / loss / backward / Adam sequence
+    replays as one launch.  Requires a fixed batch size (the short last batch of an epoch runs through ``train_step``) and an
+    optimizer built with ``capturable=True``."""
+
+    def __init__(self, model, optimizer, reg: float, batch_size: int, batch: int, forward=None, warmup: int = 3):
+        dev = next(model.parameters()).device
+        self.u = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.p = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.n = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.batch = batch
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the default stream: lazy initialisation must not land in the capture
+            for _ in range(warmup):
+                train_step(model, optimizer, self.u, self.p, self.n, reg, batch_size, forward)
+        torch.cuda.current_stream().wait_stream(side)
+        from . import _lib
+
+        before = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = train_step(model, optimizer, self.u, self.p, self.n, reg, batch_size, forward)
+        self.kernels_per_replay = _lib.launch_count() - before  # libhgr kernels inside one replay
+
+    def __call__(self, user_idx, pos_idx, neg_idx):
+        if user_idx.numel() != self.batch:
+            raise ValueError("graphed step was captured for batch %d, got %d" % (self.batch, user_idx.numel()))
+        self.u.copy_(user_idx, non_blocking=True)
+        self.p.copy_(pos_idx, non_blocking=True)
+        self.n.copy_(neg_idx, non_blocking=True)
+        self.graph.replay()
+        return self.losses
