@@ -427,3 +427,20 @@ def train_step(model, optimizer, g: DistGraph, user_idx, pos_idx, neg_idx, reg: 
         sync_replicated_grads(model, group=g.group)
     optimizer.step()
     return torch.stack([rec_loss.detach(), reg_loss.detach()])
+
+
+def fullrank_topk_sharded(g: DistGraph, out_u: torch.Tensor, out_i: torch.Tensor, test_users_local: torch.Tensor,
+                          train_indptr_own: torch.Tensor, train_indices_own: torch.Tensor, n_items: int, k: int,
+                          mode: str = "exact", engine: str = "auto", return_stats: bool = False):
+    """Full-ranking evaluation sharded by user: every rank ranks ITS users (``test_users_local`` index the
+    rank's own user rows ``out_u``; ``train_indptr_own / train_indices_own`` is the training matrix of those rows with GLOBAL
+    item ids) against the whole item table, which is assembled once from the gathered rows.  Returns this rank's
+    ``(ids, scores[, stats])`` with global item ids; recommendation lists never cross ranks (metric sums do, as scalars)."""
+    from . import evaluation
+
+    with torch.no_grad():
+        full = g.gathered(_unsplit(out_u, out_i))
+        item_tab = full[g.part.perm_item(torch.arange(n_items, device=full.device))].contiguous()  # rows back in item-id order
+        u_tab = out_u[:train_indptr_own.numel() - 1].contiguous()  # the training matrix may cover a prefix of the owned users
+        return evaluation.fullrank_topk(u_tab, item_tab, test_users_local, train_indptr_own, train_indices_own, k, mode=mode,
+                                        engine=engine, return_stats=return_stats)

@@ -7,6 +7,7 @@ keeps working when these are imported instead:
 ===========================  ==================================================================
 ``TorchGraphInterface``       base/torch_interface.py:3-19
 ``LGCN_Encoder``              model/graph/LightGCN.py:104-140
+``SGL_Encoder``               model/graph/SGL.py:110-180 (+ data/augmentor.py through ``augmentor.py``)
 ``HGCNConv``                  model/graph/HGNN_HD3.py:540-553 (18 identical copies)
 ``SpAdjDropEdge``             model/graph/HCCF.py:213-226
 ``MLP``                       model/layers/MLP.py:29-117
@@ -86,6 +87,63 @@ class LGCN_Encoder(nn.Module):
         ego_embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
         all_embeddings = ops.lightgcn_propagate(self.sparse_norm_adj, ego_embeddings, self.layers)
         return all_embeddings[:self.data.n_users], all_embeddings[self.data.n_users:]
+
+
+class SGL_Encoder(nn.Module):
+    """``SGL_Encoder`` (model/graph/SGL.py:110-180): LightGCN propagation on the clean graph or on a perturbed one (a single
+    ``DeviceCSR`` or one per layer), two augmented views per batch and ``InfoNCE`` between them.  ``data`` must expose the
+    dense-id interaction list as ``data.train_u / data.train_i`` (device int tensors) for ``graph_reconstruction``."""
+
+    def __init__(self, data, emb_size, drop_rate, n_layers, temp, aug_type):
+        super(SGL_Encoder, self).__init__()
+        self.data = data
+        self.drop_rate = drop_rate
+        self.emb_size = emb_size
+        self.n_layers = n_layers
+        self.temp = temp
+        self.aug_type = aug_type
+        self.norm_adj = data.norm_adj
+        initializer = nn.init.xavier_uniform_
+        self.embedding_dict = nn.ParameterDict({
+            'user_emb': nn.Parameter(initializer(torch.empty(self.data.n_users, self.emb_size))),
+            'item_emb': nn.Parameter(initializer(torch.empty(self.data.n_items, self.emb_size))),
+        })
+        self.sparse_norm_adj = _adjacency_of(data)
+
+    def graph_reconstruction(self):
+        # the reference's condition `self.aug_type==0 or 1` is always true: one perturbed graph for all layers
+        return self.random_graph_augment()
+
+    def random_graph_augment(self):
+        from . import augmentor
+
+        return augmentor.random_graph_augment(self.data.train_u, self.data.train_i, self.data.n_users, self.data.n_items,
+                                              self.aug_type, self.drop_rate)
+
+    def forward(self, perturbed_adj=None):
+        ego_embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
+        if perturbed_adj is None or not isinstance(perturbed_adj, list):
+            adj = self.sparse_norm_adj if perturbed_adj is None else perturbed_adj
+            all_embeddings = ops.lightgcn_propagate(adj, ego_embeddings, self.n_layers)
+        else:
+            acc = ego_embeddings
+            for k in range(self.n_layers):
+                ego_embeddings = ops.spmm(perturbed_adj[k], ego_embeddings)
+                acc = acc + ego_embeddings
+            all_embeddings = acc / (self.n_layers + 1)
+        return torch.split(all_embeddings, [self.data.n_users, self.data.n_items])
+
+    def cal_cl_loss(self, idx, perturbed_mat1, perturbed_mat2):
+        from .loss_torch import InfoNCE
+
+        dev = self.embedding_dict['user_emb'].device
+        u_idx = torch.unique(torch.as_tensor(idx[0], device=dev).long())
+        i_idx = torch.unique(torch.as_tensor(idx[1], device=dev).long())
+        user_view_1, item_view_1 = self.forward(perturbed_mat1)
+        user_view_2, item_view_2 = self.forward(perturbed_mat2)
+        view1 = torch.cat((user_view_1[u_idx], item_view_1[i_idx]), 0)
+        view2 = torch.cat((user_view_2[u_idx], item_view_2[i_idx]), 0)
+        return InfoNCE(view1, view2, self.temp)
 
 
 class HGCNConv(nn.Module):

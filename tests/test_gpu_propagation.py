@@ -303,3 +303,41 @@ def test_scatter_mean_ragged_incidence_with_empty_segments(hgr):
     conv = encoders.EquivSetConvScatter(d, d, mlp1_layers=0, mlp2_layers=0, mlp3_layers=0, aggr='mean', alpha=0.0)
     out = conv(cuda(x), torch.from_numpy(v).cuda(), torch.from_numpy(e).cuda(), cuda(x))
     assert rel_err(out, y) < 1e-6
+
+
+# ------------------------------------------------------------------------------------ SGL (augmentation + InfoNCE views)
+def test_sgl_encoder_views_and_device_augmentor(hgr, pl_graph):
+    from hypergraph_diffusion_for_recommendation_b200 import augmentor
+
+    n_users, n_items = pl_graph["n_users"], pl_graph["n_items"]
+    u, i = cuda(pl_graph["u"]), cuda(pl_graph["i"])
+    ku, ki = augmentor.GraphAugmentor.edge_dropout(u, i, 0.3)
+    assert ku.numel() == int(u.numel() * 0.7)
+    pairs = set(zip(pl_graph["u"].tolist(), pl_graph["i"].tolist()))
+    assert set(zip(ku.tolist(), ki.tolist())) <= pairs and len(set(zip(ku.tolist(), ki.tolist()))) == ku.numel()
+    nu, ni = augmentor.GraphAugmentor.node_dropout(u, i, n_users, n_items, 0.2)
+    assert n_users - len(set(nu.tolist())) >= int(n_users * 0.2) - 0 and nu.numel() < u.numel()
+    # the perturbed Laplacian is exactly the oracle's normalised adjacency of the kept interactions
+    adj = augmentor.convert_to_laplacian_mat(ku, ki, n_users, n_items)
+    want = O.build_norm_adj(ku.cpu().numpy(), ki.cpu().numpy(), n_users, n_items)
+    got = adj.to_host()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(bits(got[2]), bits(want[2]))
+    # encoder: clean forward == LightGCN; perturbed views differ; the contrastive loss is differentiable
+    n = n_users + n_items
+    data = types.SimpleNamespace(n_users=n_users, n_items=n_items, train_u=u, train_i=i, norm_adj=None,
+                                 norm_adj_device=hgr.graph.DeviceCSR.from_host(*pl_graph["csr"], (n, n), symmetric=True))
+    torch.manual_seed(0)
+    enc = hgr.enc.SGL_Encoder(data, 64, 0.2, 3, 0.2, 1).cuda()
+    ue, ie = enc()
+    ego = torch.cat([enc.embedding_dict['user_emb'], enc.embedding_dict['item_emb']], 0)
+    ref_u, ref_i = O.lgcn_forward(pl_graph["csr"], ego[:n_users].detach().cpu().numpy(), ego[n_users:].detach().cpu().numpy(), 3)
+    assert rel_err(ue, ref_u) < 1e-6 and rel_err(ie, ref_i) < 1e-6
+    p1, p2 = enc.graph_reconstruction(), enc.graph_reconstruction()
+    v1, _ = enc(p1)
+    assert not torch.equal(v1, ue)
+    loss = enc.cal_cl_loss([torch.arange(0, n_users, 2), torch.arange(0, n_items, 3)], p1, p2)
+    loss.backward()
+    assert torch.isfinite(loss) and float(enc.embedding_dict['user_emb'].grad.abs().sum()) > 0
+    # per-layer list of perturbed graphs (aug_type 2 in the paper) gives the same result as one graph used for every layer
+    a, b = enc([p1, p1, p1]), enc(p1)
+    assert rel_err(a[0], b[0]) < 1e-6
