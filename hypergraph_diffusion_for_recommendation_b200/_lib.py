@@ -51,6 +51,7 @@ SIGNATURES = {
     "hgr_spmm_f32": (C.c_int, [C.POINTER(CsrDesc), _VP, _VP, _I32, C.POINTER(Epilogue), _VP, _SZ, _VP]),
     "hgr_hgconv_f32": (C.c_int, [C.POINTER(CsrDesc), C.POINTER(CsrDesc), _VP, _VP, _VP, _I32, C.POINTER(Epilogue), _VP, _SZ, _VP]),
     "hgr_lightgcn_forward_f32": (C.c_int, [C.POINTER(CsrDesc), _VP, _VP, _VP, _I32, _I32, _I32, _VP, _SZ, _VP]),
+    "hgr_layer_norm_f32": (C.c_int, [_VP, _VP, _VP, _F32, _I64, _I32, _VP, _VP]),
     "hgr_ln_bwd_partial_rows": (_I32, [_I64]),
     "hgr_leaky_ln_bwd_f32": (C.c_int, [_VP, _VP, _VP, _F32, _I32, _F32, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
     "hgr_build_csr_workspace_bytes": (_SZ, [_I64]),

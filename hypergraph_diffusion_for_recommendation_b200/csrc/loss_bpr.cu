@@ -67,12 +67,23 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_fwd_kernel(const float4 *
 }
 
 // out[0] = rec loss, out[1] = reg loss; norms[0..2] = ||U_B||, ||P_B||, ||N_B|| (saved for backward)
-__global__ void bpr_l2_finish_kernel(const double *__restrict__ partials, int n_blocks, int64_t batch, float reg,
-                                     float batch_size_div, float *__restrict__ out, float *__restrict__ norms) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double t[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int b = 0; b < n_blocks; ++b)
-        for (int k = 0; k < 4; ++k) t[k] += partials[(size_t)b * 4 + k];
+__global__ void __launch_bounds__(256) bpr_l2_finish_kernel(const double *__restrict__ partials, int n_blocks, int64_t batch, float reg,
+                                                            float batch_size_div, float *__restrict__ out,
+                                                            float *__restrict__ norms) {
+    // thread t adds blocks t, t + 256, ... in order, then a fixed tree: deterministic
+    __shared__ double sh[4][256];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < n_blocks; b += 256)
+        for (int k = 0; k < 4; ++k) acc[k] += partials[(size_t)b * 4 + k];
+    for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w)
+            for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const double t[4] = {sh[0][0], sh[1][0], sh[2][0], sh[3][0]};
     const float nu = (float)sqrt(t[1]), np_ = (float)sqrt(t[2]), nn = (float)sqrt(t[3]);
     out[0] = batch > 0 ? (float)(t[0] / (double)batch) : 0.f;
     out[1] = (nu + np_ + nn) * reg / batch_size_div;
@@ -172,7 +183,7 @@ int hgr_bpr_l2_fwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
             bpr_l2_fwd_kernel<32><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count); break;
     }
     HGR_LAUNCH_OK("bpr_l2_fwd_kernel");
-    bpr_l2_finish_kernel<<<1, 32, 0, st>>>(partials, blocks, batch, reg, batch_size_div, out, norms);
+    bpr_l2_finish_kernel<<<1, 256, 0, st>>>(partials, blocks, batch, reg, batch_size_div, out, norms);
     HGR_LAUNCH_OK("bpr_l2_finish_kernel");
     return HGR_OK;
 }

@@ -217,12 +217,20 @@ class MLP(nn.Module):
             if not (normalization.__class__.__name__ == 'Identity'):
                 normalization.reset_parameters()
 
+    @staticmethod
+    def _norm(module, x):
+        # LayerNorm over rows of 32 / 64 / 128 floats runs on libhgr's row kernel (torch's takes 2.2 ms for 1.5 M x 64)
+        if (isinstance(module, nn.LayerNorm) and module.elementwise_affine and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+                and x.shape[1] in (32, 64, 128) and len(module.normalized_shape) == 1):
+            return ops.layer_norm(x, module.weight, module.bias, module.eps)
+        return module(x)
+
     def forward(self, x):
-        x = self.normalizations[0](x)
+        x = self._norm(self.normalizations[0], x)
         for i, lin in enumerate(self.lins[:-1]):
             x = lin(x)
             x = F.relu(x, inplace=True)
-            x = self.normalizations[i + 1](x)
+            x = self._norm(self.normalizations[i + 1], x)
             x = F.dropout(x, p=self.dropout, training=self.training)
         return self.lins[-1](x)
 

@@ -128,6 +128,10 @@ int hgr_lightgcn_forward_f32(const hgr_csr_t *A, const float *E0, float *layers,
  * excluded): dpre from dy.  dgamma/dbeta are accumulated per block into `partials`
  * ([hgr_ln_bwd_partial_rows(n_rows), 2, D]) and reduced in a fixed order by the second kernel, so
  * the result is deterministic.  gamma == NULL means "no LayerNorm" (only the leaky slope applies). */
+/* y = LayerNorm(x) * gamma + beta over rows of D floats (torch.nn.LayerNorm(D), e.g. the MLP input norm of EquivSetConv,
+ * model/layers/MLP.py:109-110); its backward is hgr_leaky_ln_bwd_f32 with pre = x and use_leaky = 0. */
+int hgr_layer_norm_f32(const float *x, const float *gamma, const float *beta, float ln_eps, int64_t n_rows, int32_t D, float *y,
+                       hgr_stream_t stream);
 int32_t hgr_ln_bwd_partial_rows(int64_t n_rows);
 int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
                          float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
