@@ -37,6 +37,13 @@ WORKLOADS = {
     "c3": (30_000, 41_000, 1_000_000, 4096, False),
     "c2": (6_040, 3_706, 750_000, 2048, False),
 }
+WORKLOAD_NOTE = {
+    "c5w": "BASELINE configs[4] (10 M x 2 M x 1 B, hypergraph-diffusion encoder, row-sharded over 8 GPUs) weak-scaled: every GPU holds 1/8 of it, "
+           "N = 8 is the configuration itself; the per-GPU slice is the largest shape of the list whose tables exceed L2",
+    "c4": "BASELINE configs[3] (Amazon-Book shape, hypergraph-diffusion / EquivSetConv)",
+    "c3": "BASELINE configs[2] (Gowalla shape; --model hccf is the HCCF + hypergraph SSL configuration)",
+    "c2": "BASELINE configs[1] (ml-1m shape, LightGCN 3 layers, emb 64, 1 GPU)",
+}
 MODELS = {"hgnn_hd3": "HGNN_HD3 local encoder (EquivSetConv + HGCNConv), 2 layers", "lightgcn": "LightGCN, 3 layers",
           "hccf": "HCCF, 2 layers, 128 learned hyperedges, edge keep 0.8, contrastLoss on the batch's unique users/items (temp 0.2)"}
 HCCF_CONF = {"lrate": LR if False else 0.001, "lr_decay": 1.0, "max_epoch": 1, "batch_size": 4096, "reg": 0.0, "embedding_size": 64, "hyper_dim": 128,
@@ -421,6 +428,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if WORKLOADS[args.workload][4] else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: %d users x %d items x %d interactions, emb %d, %s, batch %d" % (args.workload, U, I, E, D, MODELS[args.model], B),
+                       "baseline_config": WORKLOAD_NOTE[args.workload],
                        "steps_per_epoch": steps_per_epoch, "nnz": nnz,
                        "l2": "flushed between steps (256 MiB write)" if small else "inputs larger than L2 (CSR %.1f GB + tables %.2f GB)" % (nnz * 8 / 1e9, (U + I) * D * 4 / 1e9),
                        "cuda_graph": bool(use_graph),
