@@ -46,7 +46,7 @@ WORKLOAD_NOTE = {
 }
 MODELS = {"hgnn_hd3": "HGNN_HD3 local encoder (EquivSetConv + HGCNConv), 2 layers", "lightgcn": "LightGCN, 3 layers",
           "hccf": "HCCF, 2 layers, 128 learned hyperedges, edge keep 0.8, contrastLoss on the batch's unique users/items (temp 0.2)"}
-HCCF_CONF = {"lrate": LR if False else 0.001, "lr_decay": 1.0, "max_epoch": 1, "batch_size": 4096, "reg": 0.0, "embedding_size": 64, "hyper_dim": 128,
+HCCF_CONF = {"lrate": 0.001, "lr_decay": 1.0, "max_epoch": 1, "batch_size": 4096, "reg": 0.0, "embedding_size": 64, "hyper_dim": 128,
              "drop_rate": 0.2, "p": 0.5, "n_layers": 2}
 HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP = 0.2, 0.1, 0.8
 D = 64
@@ -228,7 +228,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from hypergraph_diffusion_for_recommendation_b200 import _lib, encoders, ops, trainer
-    from hypergraph_diffusion_for_recommendation_b200.synth import norm_adj_from_pairs_torch, powerlaw_interactions_device
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -210,8 +210,6 @@ def _as_i32(x, device) -> torch.Tensor:
 
 
 def _build(kind: str, a: torch.Tensor, b: torch.Tensor, n_rows: int, n_cols: int, n_users: int = 0, n_items: int = 0):
-    import ctypes as C
-
     dev = a.device
     if dev.type != "cuda":
         raise _lib.HgrError("graph construction runs on the GPU (no CPU path)")

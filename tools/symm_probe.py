@@ -1,7 +1,5 @@
 """Probe: does torch symmetric memory (peer-mapped buffers over NVLink) work on this box?  Run under torchrun."""
 import os
-import sys
-import time
 
 import torch
 import torch.distributed as dist
