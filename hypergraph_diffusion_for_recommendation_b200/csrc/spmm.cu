@@ -289,29 +289,43 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_async_kernel(hgr_csr
     finish_row<LPR>(acc, row, gl, gmask, ep, Y);
 }
 
+// One block per split row: group g adds the partial rows of chunks g, g + GPB, ... in order, group 0 then adds the GPB
+// group sums in group order and runs the epilogue.  A fixed order (deterministic), and the most popular item's ~1 200
+// chunks are no longer walked by a single group.
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A, const float4 *__restrict__ partials,
                                                                      float *__restrict__ Y, hgr_epilogue_t ep) {
     constexpr int GPB = kThreads / LPR;
+    __shared__ float4 sh[kThreads];
     const int gl = threadIdx.x % LPR;
+    const int g = threadIdx.x / LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
-    const int h = blockIdx.x * GPB + threadIdx.x / LPR;
-    if (h >= A.n_heavy_rows) return;
+    const int h = blockIdx.x;
     const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = c0; c < c1; c += kUnroll) {
+    for (int64_t c = c0 + g; c < c1; c += (int64_t)GPB * kUnroll) {
         float4 p[kUnroll];
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k)
-            if (c + k < c1) p[k] = ld_stream_f4(partials + (c + k) * LPR + gl);
+            if (c + (int64_t)k * GPB < c1) p[k] = ld_stream_f4(partials + (c + (int64_t)k * GPB) * LPR + gl);
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k)
-            if (c + k < c1) {
+            if (c + (int64_t)k * GPB < c1) {
                 acc.x += p[k].x;
                 acc.y += p[k].y;
                 acc.z += p[k].z;
                 acc.w += p[k].w;
             }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (g != 0) return;
+    for (int k = 1; k < GPB; ++k) {
+        const float4 q = sh[k * LPR + gl];
+        acc.x += q.x;
+        acc.y += q.y;
+        acc.z += q.z;
+        acc.w += q.w;
     }
     finish_row<LPR>(acc, A.heavy_rows[h], gl, gmask, ep, Y);
 }
@@ -355,7 +369,7 @@ static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_e
                                                                           reinterpret_cast<float4 *>(ws), (int)heavy_blocks);
     HGR_LAUNCH_OK("spmm_rows_kernel");
     if (A.n_heavy_rows > 0) {
-        spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, GPB), kThreads, 0, st>>>(
+        spmm_heavy_reduce_kernel<LPR><<<(unsigned)A.n_heavy_rows, kThreads, 0, st>>>(
             A, reinterpret_cast<const float4 *>(ws), Y, ep);
         HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
     }
@@ -376,7 +390,7 @@ static int launch_spmm_async(const hgr_csr_t &A, const float *X, float *Y, const
                                                                                  partials, (int)heavy_blocks);
     HGR_LAUNCH_OK("spmm_rows_async_kernel");
     if (A.n_heavy_rows > 0) {
-        spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, GPB), kThreads, 0, st>>>(A, partials, Y, ep);
+        spmm_heavy_reduce_kernel<LPR><<<(unsigned)A.n_heavy_rows, kThreads, 0, st>>>(A, partials, Y, ep);
         HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
     }
     return HGR_OK;
