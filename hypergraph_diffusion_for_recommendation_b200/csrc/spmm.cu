@@ -28,7 +28,7 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 8;  // partial-row reduce kernel
 
 // Tuning variant (unroll depth of the gather batch x resident blocks per SM); see hgr_set_spmm_variant.
-static int g_variant = 0;  // 0 = cp.async ring of 2 x 4 rows per group, 6 blocks/SM
+static int g_variant = 0;  // 0 = cp.async ring of 2 x 4 rows per group, 5 blocks/SM
 
 template <int LPR, int UNR>
 __device__ __forceinline__ float4 gather_accumulate(const int32_t *__restrict__ idx, const float *__restrict__ val,
@@ -410,7 +410,11 @@ static int launch_spmm_variant(const hgr_csr_t &A, const float *X, float *Y, con
         case 6: return launch_spmm_async<LPR, 8, 3>(A, X, Y, ep, ws, st);
         case 7: return launch_spmm_async<LPR, 2, 8>(A, X, Y, ep, ws, st);
         case 8: return launch_spmm_async<LPR, 4, 7>(A, X, Y, ep, ws, st);
-        default: return launch_spmm_async<LPR, 4, 6>(A, X, Y, ep, ws, st);
+        case 9: return launch_spmm_async<LPR, 4, 6>(A, X, Y, ep, ws, st);
+        case 10: return launch_spmm_async<LPR, 4, 4>(A, X, Y, ep, ws, st);
+        // 5 resident blocks leave 48 registers per thread: the 2 x 4 ring compiles without the spills it has under the
+        // 40-register cap of 6 blocks, +9 % on both shapes (profiles/spmm_variants_r1.md)
+        default: return launch_spmm_async<LPR, 4, 5>(A, X, Y, ep, ws, st);
     }
 }
 
@@ -445,7 +449,7 @@ static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, co
 extern "C" {
 
 int hgr_set_spmm_variant(int variant) {
-    HGR_REQUIRE(variant >= 0 && variant <= 8, "variant %d out of range", variant);
+    HGR_REQUIRE(variant >= 0 && variant <= 10, "variant %d out of range", variant);
     hgr::g_variant = variant;
     return HGR_OK;
 }

@@ -102,8 +102,8 @@ typedef struct {
  * `workspace` must hold hgr_spmm_workspace_bytes(A, D) bytes (0 when the plan has no heavy rows).
  * `epi` may be NULL.  Deterministic: the same inputs give the same bits on every run. */
 size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D);
-/* Tuning hook of the propagation kernel (gather depth x resident blocks per SM).  0 [default], 6, 7, 8: embedding rows
- * staged through a shared-memory ring with cp.async (2x4 x 6, 2x8 x 3, 2x2 x 8, 2x4 x 7); 1-5: register gathers
+/* Tuning hook of the propagation kernel (gather depth x resident blocks per SM).  0 [default], 6, 7, 8, 9, 10: embedding
+ * rows staged through a shared-memory ring with cp.async (2x4 x 5, 2x8 x 3, 2x2 x 8, 2x4 x 7, 2x4 x 6, 2x4 x 4); 1-5: register gathers
  * (8 x 3, 8 x 4, 4 x 5, 2 x 8, 4 x 6).  Results do not depend on it. */
 int hgr_set_spmm_variant(int variant);
 int hgr_spmm_f32(const hgr_csr_t *A, const float *X, float *Y, int32_t D, const hgr_epilogue_t *epi,

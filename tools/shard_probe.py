@@ -1,0 +1,57 @@
+"""The propagation kernel on ONE rank's block of the row-partitioned 10 M x 2 M x 1 B graph (BASELINE configs[4]), run on a
+single GPU without any communication, so that it can be profiled with ncu (multi-rank commands cannot):
+
+    python tools/shard_probe.py [--world 8] [--rank 0] [--iters 5]
+
+The block is A[own rows, :] with 1.5 M rows, ~250 M nonzeros and 12 M columns; X is the gathered [12 M, 64] table (3 GB)."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hypergraph_diffusion_for_recommendation_b200 import dist as hdist  # noqa: E402
+from hypergraph_diffusion_for_recommendation_b200 import ops  # noqa: E402
+from hypergraph_diffusion_for_recommendation_b200.graph import DeviceCSR  # noqa: E402
+from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--world", type=int, default=8)
+    ap.add_argument("--rank", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=5)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    U, I, E = 1_250_000 * args.world, 250_000 * args.world, 125_000_000 * args.world
+    t0 = time.time()
+    u, i = powerlaw_interactions_device(U, I, E, dev, seed=1234)
+    part = hdist.Partition(U, I, args.world)
+    indptr, indices, values = hdist.local_block(part, args.rank, u, i)
+    del u, i
+    torch.cuda.empty_cache()
+    block = DeviceCSR(indptr, indices, values, (part.n_loc, part.n_glob))
+    torch.cuda.synchronize()
+    print("block %d of %d: rows %d cols %d nnz %d, heavy rows %d, built in %.1f s" % (
+        args.rank, args.world, part.n_loc, part.n_glob, block._nnz(), block.desc.n_heavy_rows, time.time() - t0), flush=True)
+    x = torch.randn(part.n_glob, 64, device=dev)
+    for _ in range(2):
+        y = ops.spmm_raw(block, x)
+    ts = []
+    for _ in range(args.iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        y = ops.spmm_raw(block, x)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts) // 2]
+    nnz = block._nnz()
+    alg = 8 * (part.n_loc + 1) + 8 * nnz + 256 * nnz + 256 * part.n_loc
+    print("spmm median %.3f ms | %.1f Gnnz/s | algorithmic %.1f GB -> %.0f GB/s" % (ms, nnz / ms / 1e6, alg / 1e9, alg / ms / 1e6), flush=True)
+
+
+if __name__ == "__main__":
+    main()
