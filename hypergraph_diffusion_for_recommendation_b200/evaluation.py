@@ -72,6 +72,12 @@ class EvalData:
     def __init__(self, data, device="cuda"):
         dev = torch.device(device)
         self.data = data
+        if hasattr(data, "eval_arrays"):  # the array-backed façade (data.Interaction): no python loop over interactions
+            users, self.raw_users, self.truth_indptr, self.truth_items, self.id2item = data.eval_arrays()
+            self.test_users = torch.from_numpy(users.astype(np.int32)).to(dev)
+            mask = data.interaction_mat  # DeviceCSR, user -> sorted training items
+            self.train_indptr, self.train_indices = mask.indptr, mask.indices
+            return
         self.raw_users = list(data.test_set.keys())
         self.test_users = torch.tensor([data.user[u] for u in self.raw_users], dtype=torch.int32, device=dev)
         mat = data.interaction_mat.tocsr()

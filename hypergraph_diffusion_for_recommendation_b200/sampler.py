@@ -37,6 +37,9 @@ class PairwiseSampler:
     @classmethod
     def from_interaction(cls, data, device="cuda", seed: int = 0):
         """From the reference's ``Interaction`` (data/ui_graph.py): ``training_data`` rows are ``[raw_user, raw_item, w]``."""
+        if hasattr(data, "dense_training_pairs"):  # the array-backed façade (data.Interaction)
+            u, i = data.dense_training_pairs()
+            return cls(u, i, data.n_users, data.n_items, device=device, seed=seed)
         u = np.fromiter((data.user[int(e[0])] for e in data.training_data), dtype=np.int64, count=len(data.training_data))
         i = np.fromiter((data.item[int(e[1])] for e in data.training_data), dtype=np.int64, count=len(data.training_data))
         return cls(u, i, data.n_users, data.n_items, device=device, seed=seed)

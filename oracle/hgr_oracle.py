@@ -421,3 +421,45 @@ def ranking_evaluation(test_items, rec_ids, top_n):
         out.append("Recall:" + str(round(sum(recall_list) / len(recall_list), 5)) + "\n")
         out.append("NDCG:" + str(round(ndcg_sum / len(hits), 5)) + "\n")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ data layer
+def load_data_set(path):
+    """``FileIO.load_data_set`` (data/loader.py:24-38): header skipped, tab-or-comma split per line, weight 1."""
+    from re import split
+
+    data = []
+    with open(path) as f:
+        next(f)
+        for line in f:
+            items = split(',', line.strip()) if '\t' not in line else split('\t', line.strip())
+            data.append([int(items[0]), int(items[1]), 1.0])
+    return data
+
+
+def generate_set(training_data, test_data):
+    """``Interaction.__generate_set`` (data/ui_graph.py:43-68), the python loop itself: dense ids by first appearance,
+    dict-of-dict training / test sets (a rewritten pair keeps its slot and takes the new rating), ``user_history_dict``
+    lists for rating-1 entries, test entries of unknown users skipped.  Returns plain dicts / a set."""
+    user, item, id2user, id2item = {}, {}, {}, {}
+    training_set_u, training_set_i, test_set, history = {}, {}, {}, {}
+    test_set_item = set()
+    for u, i, r in training_data:
+        u, i = int(u), int(i)
+        if u not in user:
+            user[u] = len(user)
+            id2user[user[u]] = u
+        if i not in item:
+            item[i] = len(item)
+            id2item[item[i]] = i
+        if r == 1.0:
+            history.setdefault(u, []).append(i)
+        training_set_u.setdefault(u, {})[i] = r
+        training_set_i.setdefault(i, {})[u] = r
+    for u, i, r in test_data:
+        if u not in user:
+            continue
+        test_set.setdefault(u, {})[i] = r
+        test_set_item.add(i)
+    return dict(user=user, item=item, id2user=id2user, id2item=id2item, training_set_u=training_set_u,
+                training_set_i=training_set_i, test_set=test_set, user_history_dict=history, test_set_item=test_set_item)
