@@ -54,7 +54,7 @@ REG = 0.01
 LR = 0.001
 CPU_SAMPLE_DIV = {"c5w": 64, "c4": 1, "c3": 1, "c2": 1}
 # dram__bytes_read.sum + dram__bytes_write.sum of one spmm_rows_async_kernel launch (ncu --set full, profiles/spmm_r1.md)
-SPMM_DRAM_TRAFFIC = {("c5w", 1): 20.32e9, ("c4", 1): 99.8e6}
+SPMM_DRAM_TRAFFIC = {("c5w", 1): 19.96e9, ("c4", 1): 99.8e6}
 
 
 def parse_args():
@@ -411,12 +411,12 @@ def run_ours(args):
     avg_ms = sum(spmm_ms) / max(len(spmm_ms), 1)
     achieved = alg / (avg_ms * 1e-3) / 1e9 if spmm_ms else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": SPMM_DRAM_TRAFFIC.get((args.workload, world)), "kernel": "spmm_rows_async_kernel<16,4,6> (+ spmm_heavy_reduce_kernel)", "launch_ms": avg_ms,
+                "traffic": SPMM_DRAM_TRAFFIC.get((args.workload, world)), "kernel": "spmm_rows_async_kernel<16,4,5> (+ spmm_heavy_reduce_kernel)", "launch_ms": avg_ms,
                 "launches_timed": len(spmm_ms), "algorithmic_bytes": alg, "peak_source": peak_src,
                 "spmm_share_of_step": ((2 * len(spmm_ms) / 3 * avg_ms) / ms_per_step if graphed is not None else sum(spmm_ms) / total_ms) if spmm_ms else None,
                 "note": "algorithmic bytes charge one 256-B row per nonzero to HBM (SURVEY.md 8d); the power-law graph lets L2 absorb "
                         "about two thirds of that (traffic = dram bytes per launch from ncu, profiles/spmm_r1.md), so achieved can exceed the "
-                        "copy peak; the kernel runs at ~84 % of the L2 -> SM fabric cap (10 TB/s of 256-B row gathers)"}
+                        "copy peak; ncu: 66.9 GB from L2 to the SMs in 6.0 ms = 5 940 B/clk, ~94 % of the ~6 300 B/clk L2-slice cap; DRAM at 51 % of the copy peak"}
 
     if rank == 0:
         cpu = None

@@ -339,8 +339,12 @@ class Interaction(Data):
                 m = graph.build_norm_adj(u, i, nu, ni, device=dev, normalize=False)
             elif name == "norm_adj":
                 m = graph.build_norm_adj(u, i, nu, ni, device=dev)
+            elif name.startswith("norm_"):
+                # normalize_graph_mat picks its branch by SHAPE (data/graph.py:14-24): with as many users as items the
+                # interaction matrix is "square" and gets D^-1/2 R D^-1/2 with the ROW sums on both sides, else D^-1 R
+                m = self.normalize_graph_mat(self._mat(name[5:]))
             else:
-                m = graph.build_interaction_csr(u, i, nu, ni, device=dev, transpose="inv" in name, row_normalize=name.startswith("norm"))
+                m = graph.build_interaction_csr(u, i, nu, ni, device=dev, transpose="inv" in name)
             self._mats[name] = m
         return m
 

@@ -69,8 +69,9 @@ def main():
         os.remove(os.path.join(tmp, name))
     os.rmdir(tmp)
 
-    # a second, weighted case that never goes through the loader: ratings other than 1 and a rewritten pair
-    weighted_train = [[1, 5, 1.0], [2, 5, 0.5], [1, 6, 2.0], [1, 5, 3.0], [2, 6, 1.0], [1, 6, 1.0]]
+    # a second, weighted case that never goes through the loader: ratings other than 1 and a rewritten pair; 2 users x 3 items, so
+    # normalize_graph_mat takes its rectangular branch (the tab case has 5 users and 5 items: the SQUARE branch, data/graph.py:14-19)
+    weighted_train = [[1, 5, 1.0], [2, 5, 0.5], [1, 6, 2.0], [1, 5, 3.0], [2, 6, 1.0], [1, 6, 1.0], [2, 7, 1.0]]
     weighted_test = [[2, 5, 1.0], [1, 9, 4.0], [1, 9, 2.0]]
     cases = {"tab": (loaded["train_tab.txt"], loaded["test_tab.txt"]), "weighted": (weighted_train, weighted_test)}
     out, arrays = {"files": files, "loaded": loaded, "cases": {}}, {}

@@ -128,6 +128,31 @@ def test_interaction_against_the_loop_restatement_on_random_lists():
         assert id2item.tolist() == [ref["id2item"][k] for k in range(len(ref["item"]))]
 
 
+@pytest.mark.parametrize("case", ["tab", "weighted"])
+def test_oracle_matrices_match_the_reference(gold, gold_arrays, case):
+    """The oracle's builders against the reference's five matrices, including the shape-picked branch of
+    normalize_graph_mat (tab: 5 users x 5 items -> the square branch on the interaction matrix)."""
+    g = gold["cases"][case]
+    d = D.Interaction(None, g["train"], g["test"])
+    u, i = d.dense_training_pairs()
+    nu, ni = d.n_users, d.n_items
+
+    def same(got, name):
+        for a, key in zip(got, ("indptr", "indices", "values")):
+            want = gold_arrays["%s_%s_%s" % (case, name, key)]
+            assert np.array_equal(np.asarray(a, dtype=want.dtype).view(np.uint32 if key == "values" else want.dtype),
+                                  want.view(np.uint32 if key == "values" else want.dtype)), (name, key)
+
+    same(O.bipartite_adjacency(u, i, nu, ni), "ui_adj")
+    same(O.build_norm_adj(u, i, nu, ni), "norm_adj")
+    r = O.interaction_matrix(u, i, nu, ni)
+    rt = O.interaction_matrix(i, u, ni, nu)
+    same(r, "interaction_mat")
+    same(rt, "inv_interaction_mat")
+    same(O.normalize_graph_mat(*r, ni), "norm_interaction_mat")
+    same(O.normalize_graph_mat(*rt, nu), "norm_inv_interaction_mat")
+
+
 def test_matrices_fail_loudly_without_a_gpu(gold):
     import torch
 
