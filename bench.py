@@ -215,7 +215,7 @@ def run_reference(args):
         "cpu_baseline": {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["epoch_s"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -375,14 +375,14 @@ def run_ours(args):
     if not args.no_clocks:
         clocks.start()
     if world > 1:
-        adj.n_fused = adj.n_collective = 0
+        adj.n_fused = adj.n_collective = adj.n_published = 0
     total_ms, losses, launches = timed("device")
     clock_info = clocks.stop()
     exchange = None
     if world > 1:
         # per step: propagations whose all-gather rode on the kernel epilogue (peer stores) vs NCCL collectives
         exchange = {"fused_gathers_per_step": adj.n_fused / (args.steps + args.warmup), "nccl_gathers_per_step": adj.n_collective / (args.steps + args.warmup),
-                    "fused": bool(adj.fused)}
+                    "copy_kernel_gathers_per_step": adj.n_published / (args.steps + args.warmup), "fused": bool(adj.fused)}
     e2e_ms, _, _ = timed("e2e")
     eval_info = run_eval(model, eval_inputs, part, adj, world, rank, dev, barrier)
 
@@ -441,7 +441,7 @@ def run_ours(args):
                                                          "what": "device COO -> normalised CSR + split plan (graph.build_norm_adj), one synchronisation"},
             "loss": [float(x) for x in losses.tolist()],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -539,8 +539,31 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
                 "metrics_s": measure_s}
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with printf when the
+    first communicator comes up), so everything else is sent to stderr and the line goes out through a saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

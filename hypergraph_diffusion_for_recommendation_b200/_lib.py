@@ -38,6 +38,20 @@ class Epilogue(C.Structure):
     ]
 
 
+class Gather(C.Structure):
+    """hgr_gather_t"""
+    _fields_ = [("n_gather", C.c_int32), ("out", C.c_void_p * HGR_MAX_GATHER), ("row_offset", C.c_int64)]
+
+
+def make_gather(ptrs, row_offset: int) -> Gather:
+    g = Gather()
+    g.n_gather = len(ptrs)
+    for j, p in enumerate(ptrs):
+        g.out[j] = int(p)
+    g.row_offset = int(row_offset)
+    return g
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/hgr.h declares
@@ -54,6 +68,8 @@ SIGNATURES = {
     "hgr_layer_norm_f32": (C.c_int, [_VP, _VP, _VP, _F32, _I64, _I32, _VP, _VP]),
     "hgr_ln_bwd_partial_rows": (_I32, [_I64]),
     "hgr_leaky_ln_bwd_f32": (C.c_int, [_VP, _VP, _VP, _F32, _I32, _F32, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "hgr_leaky_ln_bwd_gather_f32": (C.c_int, [_VP, _VP, _VP, _F32, _I32, _F32, _I64, _I32, _VP, _VP, _VP, _VP, C.POINTER(Gather), _VP]),
+    "hgr_publish_rows_f32": (C.c_int, [_VP, _I64, _I32, C.POINTER(Gather), _VP]),
     "hgr_build_csr_workspace_bytes": (_SZ, [_I64]),
     "hgr_coo_to_csr": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "hgr_bipartite_to_csr": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(kRwThreads) leaky_ln_bwd_kernel(const float4 *
                                                                    const float *__restrict__ gamma, float eps,
                                                                    int use_leaky, float slope, int64_t n_rows,
                                                                    float4 *__restrict__ dpre,
-                                                                   float *__restrict__ partials) {
+                                                                   float *__restrict__ partials, hgr_gather_t gt) {
     constexpr int GPB = kRwThreads / LPR;
     constexpr int D = LPR * 4;
     constexpr float kInvD = 1.0f / (float)D;
@@ -69,6 +69,12 @@ __global__ void __launch_bounds__(kRwThreads) leaky_ln_bwd_kernel(const float4 *
             da.w = p.w > 0.f ? da.w : da.w * slope;
         }
         dpre[off] = da;
+        if (gt.n_gather > 0) {  // fused all-gather: the row into every rank's gathered table (peer-mapped memory)
+            const int64_t goff = (gt.row_offset + row) * LPR + gl;
+#pragma unroll
+            for (int p = 0; p < HGR_MAX_GATHER; ++p)  // constant indices keep gt in param space
+                if (p < gt.n_gather) reinterpret_cast<float4 *>(gt.out[p])[goff] = da;
+        }
     }
     if (!gamma) return;
     // block reduction over the GPB groups in group order
@@ -138,6 +144,26 @@ __global__ void __launch_bounds__(kRwThreads) layer_norm_fwd_kernel(const float4
     }
 }
 
+// x[n_rows, D] -> row row_offset + r of every destination table (grid-stride over 128-bit words)
+__global__ void __launch_bounds__(kRwThreads) publish_rows_kernel(const float4 *__restrict__ x, int64_t n_words, int64_t word_offset,
+                                                                   hgr_gather_t gt) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        const float4 v = ld_stream_f4(x + w);
+#pragma unroll
+        for (int p = 0; p < HGR_MAX_GATHER; ++p)
+            if (p < gt.n_gather) reinterpret_cast<float4 *>(gt.out[p])[word_offset + w] = v;
+    }
+}
+
+static int check_gather(const hgr_gather_t *g) {
+    HGR_REQUIRE(g != nullptr, "gather is NULL");
+    HGR_REQUIRE(g->n_gather >= 0 && g->n_gather <= HGR_MAX_GATHER, "gather: n_gather %d out of range", g->n_gather);
+    HGR_REQUIRE(g->row_offset >= 0, "gather: negative row_offset");
+    for (int j = 0; j < g->n_gather; ++j) HGR_REQUIRE(g->out[j] && aligned16(g->out[j]), "gather: table %d NULL or misaligned", j);
+    return HGR_OK;
+}
+
 }  // namespace hgr
 
 extern "C" {
@@ -152,7 +178,37 @@ int32_t hgr_ln_bwd_partial_rows(int64_t n_rows) {
 int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
                          float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
                          float *partials, hgr_stream_t stream) {
+    hgr_gather_t none;
+    none.n_gather = 0;
+    none.row_offset = 0;
+    return hgr_leaky_ln_bwd_gather_f32(pre, dy, gamma, ln_eps, use_leaky, leaky_slope, n_rows, D, dpre, dgamma, dbeta, partials, &none,
+                                       stream);
+}
+
+int hgr_publish_rows_f32(const float *x, int64_t n_rows, int32_t D, const hgr_gather_t *gather, hgr_stream_t stream) {
     using namespace hgr;
+    HGR_REQUIRE(D > 0 && D % 4 == 0, "D = %d must be a positive multiple of 4", D);
+    HGR_REQUIRE(n_rows >= 0, "n_rows negative");
+    int rc = check_gather(gather);
+    if (rc) return rc;
+    if (n_rows == 0 || gather->n_gather == 0) return HGR_OK;
+    HGR_REQUIRE(x && aligned16(x), "x is NULL or misaligned");
+    const int64_t n_words = n_rows * (D / 4);
+    int64_t blocks = ceil_div(n_words, kRwThreads * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    publish_rows_kernel<<<(unsigned)blocks, kRwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(x), n_words,
+                                                                                 gather->row_offset * (D / 4), *gather);
+    HGR_LAUNCH_OK("publish_rows_kernel");
+    return HGR_OK;
+}
+
+int hgr_leaky_ln_bwd_gather_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
+                                float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
+                                float *partials, const hgr_gather_t *gather, hgr_stream_t stream) {
+    using namespace hgr;
+    int grc = check_gather(gather);
+    if (grc) return grc;
+    const hgr_gather_t gt = *gather;
     HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
     HGR_REQUIRE(n_rows >= 0, "n_rows negative");
     if (n_rows == 0) return HGR_OK;
@@ -165,9 +221,9 @@ int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, 
     const float4 *p4 = reinterpret_cast<const float4 *>(pre), *g4 = reinterpret_cast<const float4 *>(dy);
     float4 *o4 = reinterpret_cast<float4 *>(dpre);
     switch (D) {
-        case 32: leaky_ln_bwd_kernel<8><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials); break;
-        case 64: leaky_ln_bwd_kernel<16><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials); break;
-        default: leaky_ln_bwd_kernel<32><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials); break;
+        case 32: leaky_ln_bwd_kernel<8><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials, gt); break;
+        case 64: leaky_ln_bwd_kernel<16><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials, gt); break;
+        default: leaky_ln_bwd_kernel<32><<<blocks, kRwThreads, 0, st>>>(p4, g4, gamma, ln_eps, use_leaky, leaky_slope, n_rows, o4, partials, gt); break;
     }
     HGR_LAUNCH_OK("leaky_ln_bwd_kernel");
     if (gamma) {

@@ -389,15 +389,22 @@ class Interaction(Data):
                                chunk_nnz=adj_mat.chunk_nnz)
 
     def convert_to_laplacian_mat(self, adj_mat):
-        """data/ui_graph.py:86-93: the normalised ``(U+I)^2`` adjacency of a (perturbed) ``[U, I]`` interaction matrix."""
+        """data/ui_graph.py:86-93: the normalised ``(U+I)^2`` adjacency of a (perturbed) ``[U, I]`` interaction matrix, whose
+        VALUES are carried over (a pair that was listed twice in training weighs 2).  Entries with value 0 stand for
+        dropped edges (``DeviceCSR.with_values``) and vanish, as they do from scipy's ``.nonzero()``."""
         import torch
 
         from . import graph
 
-        rows = torch.repeat_interleave(torch.arange(adj_mat.shape[0], device=adj_mat.device, dtype=torch.int32),
-                                       adj_mat.indptr[1:] - adj_mat.indptr[:-1])
-        keep = adj_mat.values != 0  # scipy's .nonzero() drops explicit zeros
-        return graph.build_norm_adj(rows[keep], adj_mat.indices[keep], adj_mat.shape[0], adj_mat.shape[1], device=adj_mat.device)
+        n_u, n_i = adj_mat.shape
+        rows = torch.repeat_interleave(torch.arange(n_u, device=adj_mat.device, dtype=torch.int32), adj_mat.indptr[1:] - adj_mat.indptr[:-1])
+        keep = adj_mat.values != 0
+        r, c, v = rows[keep], adj_mat.indices[keep], adj_mat.values[keep]
+        pattern = graph.build_norm_adj(r, c, n_u, n_i, device=adj_mat.device, normalize=False)  # unit weights, canonical CSR
+        # user rows keep the order of adj_mat's rows; item rows list the same entries sorted by (item, user)
+        vals = torch.cat([v, v[torch.sort(c, stable=True).indices]])
+        return self.normalize_graph_mat(graph.DeviceCSR(pattern.indptr, pattern.indices, vals, pattern.shape, symmetric=True,
+                                                        chunk_nnz=pattern.chunk_nnz))
 
     # ---- accessors (data/ui_graph.py:114-178) -----------------------------------------------------------------------
     def get_user_id(self, u):

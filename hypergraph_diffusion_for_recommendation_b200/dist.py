@@ -118,10 +118,16 @@ class LibhgrKernels:
         return ops.spmm_raw(block, x, ops.make_epilogue(**ep) if ep else None, no_local_out=no_local_out)
 
     @staticmethod
-    def leaky_ln_bwd(pre, dy, gamma, eps, slope):
+    def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0):
         from . import ops
 
-        return ops.leaky_ln_bwd(pre, dy, gamma, eps, slope)
+        return ops.leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs, gather_row_offset)
+
+    @staticmethod
+    def publish_rows(x, gather_ptrs, gather_row_offset):
+        from . import ops
+
+        ops.publish_rows(x, gather_ptrs, gather_row_offset)
 
 
 class SymmetricPool:
@@ -202,7 +208,8 @@ class DistGraph:
                       and os.environ.get("HGR_FUSED_GATHER", "1") != "0")
         self._pools = {}     # D -> SymmetricPool
         self._published = {}  # pool slot -> (tensor kept alive, version): local rows whose gathered copy sits in that slot
-        self.n_fused, self.n_collective = 0, 0
+        self.publish_copy = os.environ.get("HGR_PUBLISH_COPY", "1") != "0"
+        self.n_fused, self.n_collective, self.n_published = 0, 0, 0
 
     def _nnz(self):
         return self._nnz_local
@@ -244,13 +251,41 @@ class DistGraph:
         self.n_fused += 1
         return pool.bufs[k], y
 
+    def leaky_ln_bwd_published(self, pre, dy, gamma, eps, slope):
+        """LayerNorm / LeakyReLU backward whose ``dz`` rows land in every rank's gathered table as they are computed (the
+        sharded backward propagation that follows needs exactly that table).  Returns ``(dz, dgamma, dbeta, gathered dz)``."""
+        pool = self.pool(dy.shape[1])
+        k = pool.take()
+        self._published.pop(k, None)
+        dz, dgamma, dbeta = self.k.leaky_ln_bwd(pre, dy, gamma, eps, slope, pool.ptrs[k], self.rank * self.part.n_loc)
+        pool.barrier(k)
+        self._published[k] = (dz, dz._version)
+        self.n_fused += 1
+        return dz, dgamma, dbeta, pool.bufs[k]
+
+    def publish(self, x: torch.Tensor) -> torch.Tensor:
+        """Rows that do not come out of a libhgr kernel (dense layers, elementwise ops): one copy kernel stores them into
+        every rank's table over NVLink (757 GB/s measured at 2 ranks against 428 GB/s for the NCCL all_gather)."""
+        pool = self.pool(x.shape[1])
+        k = pool.take()
+        self._published.pop(k, None)
+        self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc)
+        pool.barrier(k)
+        self._published[k] = (x, x._version)
+        self.n_published += 1
+        return pool.bufs[k]
+
     def gathered(self, x: torch.Tensor) -> torch.Tensor:
-        """Gathered table of the owned rows ``x``: the pool slot a previous propagation already filled, else a collective."""
+        """Gathered table of the owned rows ``x``: the pool slot a previous kernel already filled, else a peer-store copy
+        (``HGR_PUBLISH_COPY=0``: an NCCL collective)."""
         if self.fused:
             pool = self._pools.get(x.shape[1])
             for k, (t, ver) in self._published.items():
                 if t is x or (t.data_ptr() == x.data_ptr() and t.shape == x.shape and t._version == ver == x._version):
                     return pool.bufs[k]
+            if self.publish_copy and x.dim() == 2 and x.shape[0] == self.part.n_loc and x.dtype == torch.float32 \
+                    and x.shape[1] % 4 == 0 and self.pool(x.shape[1]) is not None:
+                return self.publish(x.contiguous())
         return self.all_gather(x)
 
     def all_gather(self, x: torch.Tensor) -> torch.Tensor:
@@ -350,14 +385,19 @@ class _DistHGConv(torch.autograd.Function):
         g = ctx.g
         dy = dy.contiguous()
         dgamma = dbeta = None
+        fused = g.fused and g.pool(dy.shape[1]) is not None
+        full_dz = None
         if pre is not None:
-            dz, dgamma, dbeta = g.k.leaky_ln_bwd(pre, dy, gamma if ctx.has_ln else None, ctx.eps, ctx.slope)
+            if fused and ctx.needs_input_grad[0]:
+                dz, dgamma, dbeta, full_dz = g.leaky_ln_bwd_published(pre, dy, gamma if ctx.has_ln else None, ctx.eps, ctx.slope)
+            else:
+                dz, dgamma, dbeta = g.k.leaky_ln_bwd(pre, dy, gamma if ctx.has_ln else None, ctx.eps, ctx.slope)
         else:
             dz = dy
         dx = None
         if ctx.needs_input_grad[0]:
-            if g.fused and g.pool(dz.shape[1]) is not None:
-                full_t, _ = g.spmm_published(g.gathered(dz), None, want_local=False)
+            if fused:
+                full_t, _ = g.spmm_published(full_dz if full_dz is not None else g.gathered(dz), None, want_local=False)
                 dx = g.k.spmm(g.block, full_t)
             else:
                 t = g.k.spmm(g.block, g.all_gather(dz))

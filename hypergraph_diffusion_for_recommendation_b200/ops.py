@@ -77,18 +77,27 @@ def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addend
 make_epilogue = _epilogue
 
 
-def leaky_ln_bwd(pre, dy, gamma, eps, slope):
+def publish_rows(x: torch.Tensor, gather_ptrs, gather_row_offset: int) -> None:
+    """``hgr_publish_rows_f32``: store the owned rows ``x`` at ``gather_row_offset`` of every (peer-mapped) gathered table."""
+    x = x.contiguous()
+    g = _lib.make_gather(gather_ptrs, gather_row_offset)
+    _lib.check(_lib.lib().hgr_publish_rows_f32(x.data_ptr(), x.shape[0], x.shape[1], C.byref(g), _lib.stream_ptr()))
+
+
+def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0):
     """Backward of ``LayerNorm(leaky_relu(pre)) * gamma + beta`` (hgr_leaky_ln_bwd_f32): returns
-    ``(dpre, dgamma, dbeta)``; ``gamma is None`` means no LayerNorm."""
+    ``(dpre, dgamma, dbeta)``; ``gamma is None`` means no LayerNorm.  ``gather_ptrs``: also publish the ``dpre`` rows into
+    every rank's gathered table (hgr_leaky_ln_bwd_gather_f32)."""
     d = dy.shape[1]
     dz = torch.empty_like(dy)
     dgamma = dbeta = parts = None
     if gamma is not None:
         dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
         parts = torch.empty((_lib.lib().hgr_ln_bwd_partial_rows(dy.shape[0]), 2, d), dtype=torch.float32, device=dy.device)
-    _lib.check(_lib.lib().hgr_leaky_ln_bwd_f32(pre.data_ptr(), dy.data_ptr(), _lib.ptr(gamma), float(eps), 0 if slope is None else 1,
-                                               0.0 if slope is None else float(slope), dy.shape[0], d, dz.data_ptr(), _lib.ptr(dgamma),
-                                               _lib.ptr(dbeta), _lib.ptr(parts), _lib.stream_ptr()))
+    g = _lib.make_gather(gather_ptrs, gather_row_offset)
+    _lib.check(_lib.lib().hgr_leaky_ln_bwd_gather_f32(pre.data_ptr(), dy.data_ptr(), _lib.ptr(gamma), float(eps), 0 if slope is None else 1,
+                                                      0.0 if slope is None else float(slope), dy.shape[0], d, dz.data_ptr(),
+                                                      _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(parts), C.byref(g), _lib.stream_ptr()))
     return dz, dgamma, dbeta
 
 

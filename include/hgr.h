@@ -137,6 +137,25 @@ int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, 
                          float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
                          float *partials, hgr_stream_t stream);
 
+/* Destination of a fused all-gather (multi-GPU, dist.py) for kernels other than the propagation: row r of the producer is
+ * ALSO stored at row row_offset + r of every table in `out` (the gathered [world * n_loc, D] buffers of all ranks,
+ * peer-mapped over NVLink), exactly like hgr_epilogue_t::gather_out.  The caller orders the peers' reads with a
+ * cross-rank barrier. */
+typedef struct {
+    int32_t n_gather;
+    float *out[HGR_MAX_GATHER];
+    int64_t row_offset;
+} hgr_gather_t;
+
+/* hgr_leaky_ln_bwd_f32 whose dpre rows -- the input of the sharded backward propagation that always follows
+ * (dist.py, _DistHGConv.backward) -- are published into every rank's gathered table by the kernel that computes them. */
+int hgr_leaky_ln_bwd_gather_f32(const float *pre, const float *dy, const float *gamma, float ln_eps, int32_t use_leaky,
+                                float leaky_slope, int64_t n_rows, int32_t D, float *dpre, float *dgamma, float *dbeta,
+                                float *partials, const hgr_gather_t *gather, hgr_stream_t stream);
+/* Plain publication of owned rows x[n_rows, D] (rows that come out of a dense layer or an elementwise op): one read, one
+ * 128-bit store per destination.  Replaces ncclAllGather for the exchanges no propagation kernel can carry. */
+int hgr_publish_rows_f32(const float *x, int64_t n_rows, int32_t D, const hgr_gather_t *gather, hgr_stream_t stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Device construction of canonical CSR matrices (columns ascending, duplicates merged).

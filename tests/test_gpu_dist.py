@@ -89,18 +89,20 @@ def _worker(rank, world, port):
         for a, xin in ((adj, own(e_glob)), (plain, own(e_glob)), (whole, e_glob.clone())):
             xin = xin.requires_grad_(True)
             gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-            before = getattr(a, "n_collective", 0)
+            before, before_pub = getattr(a, "n_collective", 0), getattr(a, "n_published", 0)
             y = chain(a, xin, gm, bt)
-            colls = getattr(a, "n_collective", 0) - before
             w = g_glob if a is whole else own(g_glob)
             m = torch.ones_like(y[:, :1]) if a is whole else live[:, None].float()
             (y * w * m).sum().backward()
+            colls = getattr(a, "n_collective", 0) - before  # forward + backward
             if a is not whole:
                 dist.all_reduce(gm.grad)
                 dist.all_reduce(bt.grad)
-            outs.append((y.detach(), xin.grad, gm.grad, bt.grad, colls))
+            outs.append((y.detach(), xin.grad, gm.grad, bt.grad, (colls, getattr(a, "n_published", 0) - before_pub)))
         (y1, dx1, dg1, db1, c1), (y2, dx2, dg2, db2, c2), (yw, dxw, dgw, dbw, _) = outs
-        assert c1 == 1 and c2 == 4, (c1, c2)  # fused: only the first input needs a collective
+        # NCCL-only: 2 gathers per convolution and direction.  Fused: none at all -- the first input is published by the copy
+        # kernel, every other table by the kernel that computes its rows (propagation epilogue, LayerNorm backward)
+        assert c1 == (0, 1) and c2 == (8, 0), (c1, c2)
         assert torch.equal(y1[live], y2[live]) and torch.equal(y1[live], own(yw)[live])
         assert torch.equal(dx1[live], dx2[live]) and _rel(dx1[live], own(dxw)[live]) < 1e-5
         assert _rel(dg1, dgw) < 1e-4 and _rel(db1, dbw) < 1e-4
