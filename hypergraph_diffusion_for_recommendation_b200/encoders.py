@@ -407,6 +407,10 @@ class HGNNLayer(nn.Module):
         self.act = nn.LeakyReLU(negative_slope=leaky)
 
     def forward(self, adj, embeds):
+        # adj [n, hyper_dim] dense learned incidence, embeds [n, D]: two tall-and-skinny products on libhgr
+        # (csrc/hyperedge.cu); widths the kernels do not cover stay on the library GEMM
+        if ops.hyperedge_supported(adj, embeds):
+            return ops.hyperedge(adj, embeds)
         return torch.mm(adj, torch.mm(adj.T, embeds))
 
 

@@ -282,3 +282,64 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
     """``torch.nn.functional.layer_norm(x, (D,), weight, bias, eps)`` for 2-D float32 CUDA rows of width 32 / 64 / 128 on the
     row-group kernels of csrc/rowwise.cu (same arithmetic as the propagation epilogue)."""
     return _LayerNorm.apply(x, weight, bias, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense learned-hyperedge propagation of HCCF (csrc/hyperedge.cu) -- HGNNLayer.forward, model/graph/HCCF.py:206-211
+# ------------------------------------------------------------------------------------------------
+def tall_skinny_tn(h: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
+    """``h.T @ e`` for ``h [n, K]``, ``e [n, D]`` with n large: every SM reduces a slice of the rows (hgr_tall_skinny_tn_f32)."""
+    n, k = h.shape
+    d = e.shape[1]
+    lib = _lib.lib()
+    t = torch.empty((k, d), dtype=torch.float32, device=h.device)
+    ws_bytes = int(lib.hgr_tall_skinny_workspace_bytes(n, k, d))
+    ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=h.device)
+    _lib.check(lib.hgr_tall_skinny_tn_f32(h.data_ptr(), e.data_ptr(), n, k, d, t.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
+    return t
+
+
+def rows_times_small(a1: torch.Tensor, a2: torch.Tensor | None, b: torch.Tensor) -> torch.Tensor:
+    """``cat([a1, a2], 1) @ b`` for a small ``b`` kept in shared memory (hgr_rows_times_small_f32)."""
+    n, k1 = a1.shape
+    k2 = 0 if a2 is None else a2.shape[1]
+    y = torch.empty((n, b.shape[1]), dtype=torch.float32, device=a1.device)
+    _lib.check(_lib.lib().hgr_rows_times_small_f32(a1.data_ptr(), k1, _lib.ptr(a2), k2, b.data_ptr(), b.shape[1], n, y.data_ptr(),
+                                                   _lib.stream_ptr()))
+    return y
+
+
+def hyperedge_supported(h: torch.Tensor, e: torch.Tensor) -> bool:
+    return (h.is_cuda and e.is_cuda and h.dtype == e.dtype == torch.float32 and h.dim() == e.dim() == 2 and h.shape[0] == e.shape[0]
+            and h.shape[1] in (32, 64, 128, 256) and e.shape[1] in (32, 64, 128))
+
+
+class _Hyperedge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, e):
+        h, e = h.contiguous(), e.contiguous()
+        t = tall_skinny_tn(h, e)
+        ctx.save_for_backward(h, e, t)
+        return rows_times_small(h, None, t)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, e, t = ctx.saved_tensors
+        dy = dy.contiguous()
+        dt = tall_skinny_tn(h, dy)
+        de = rows_times_small(h, None, dt) if ctx.needs_input_grad[1] else None
+        dh = None
+        if ctx.needs_input_grad[0]:
+            d, k = e.shape[1], h.shape[1]
+            if (2 * d * k + 64 * 2 * d) * 4 <= 200 * 1024:  # [T^T ; dT^T] and a 64-row tile of [dY | E] fit shared memory
+                dh = rows_times_small(dy, e, torch.cat([t.t(), dt.t()], 0).contiguous())  # dY T^T + E dT^T in one pass
+            else:
+                dh = rows_times_small(dy, None, t.t().contiguous()) + rows_times_small(e, None, dt.t().contiguous())
+        return dh, de
+
+
+def hyperedge(h: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
+    """``h @ (h.T @ e)``: node -> learned hyperedge -> node through the dense incidence ``h`` (HGNNLayer.forward)."""
+    if not hyperedge_supported(h, e):
+        raise ValueError("hyperedge: need float32 CUDA h [n, 32|64|128|256] and e [n, 32|64|128], got %s and %s" % (tuple(h.shape), tuple(e.shape)))
+    return _Hyperedge.apply(h, e)

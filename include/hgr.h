@@ -195,6 +195,23 @@ int hgr_csr_scale(const int64_t *indptr, const int32_t *indices, float *values, 
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Dense learned-hyperedge propagation of HCCF: HGNNLayer.forward (model/graph/HCCF.py:206-211),
+ *   edge_embeds = torch.mm(adj.T, embeds);  hyper_embeds = torch.mm(adj, edge_embeds)
+ * with adj = dropout(E0 W) [n, K] and embeds [n, D].  Two tall-and-skinny products (n = users or items):
+ *   hgr_tall_skinny_tn_f32    T[K, D] = H[n, K]^T . E[n, D]      every SM reduces a slice of the rows, partials added in
+ *                                                               block order (deterministic); K in {32, 64, 128, 256}
+ *   hgr_rows_times_small_f32  Y[n, N] = [A1[n, K1] | A2[n, K2]] . B[K1 + K2, N]   B stays in shared memory;
+ *                                                               K1 + K2 <= 256, N in {32, 64, 128, 256}; A2 may be NULL
+ * Forward: T = H^T E, Y = H T.  Backward: dT = H^T dY, dE = H dT, dH = [dY | E] [T^T ; dT^T].
+ * fp32 FMA arithmetic; agrees with torch.mm to rounding (different summation order).
+ * ------------------------------------------------------------------------------------------- */
+size_t hgr_tall_skinny_workspace_bytes(int64_t n, int32_t K, int32_t D);
+int hgr_tall_skinny_tn_f32(const float *H, const float *E, int64_t n, int32_t K, int32_t D, float *T, void *workspace,
+                           size_t workspace_bytes, hgr_stream_t stream);
+int hgr_rows_times_small_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
+                             float *Y, hgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * BPR + L2 loss fused with the embedding gathers (util/loss_torch.py:5-9,17-21 called from
  * model/graph/LightGCN.py:52-55, HGNN_HD3.py:339-343, HCCF.py:60).
  *   out[0] = mean_b -log(10e-6 + sigmoid(<U[u_b], I[p_b]> - <U[u_b], I[n_b]>))

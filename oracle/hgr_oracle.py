@@ -231,6 +231,20 @@ def local_aware_encoder(csr, ego, params, n_layers, n_users, csr_t=None):
     return ego[:n_users], ego[n_users:]
 
 
+def hyperedge(adj, emb):
+    """``HGNNLayer.forward`` (model/graph/HCCF.py:206-211): ``adj @ (adj.T @ emb)`` for the dense learned incidence
+    ``adj [n, hyper_dim]``, accumulated in float64 and rounded once (the reference's fp32 BLAS order is unspecified)."""
+    a = np.asarray(adj, dtype=np.float64)
+    return (a @ (a.T @ np.asarray(emb, dtype=np.float64))).astype(np.float32)
+
+
+def hyperedge_grads(adj, emb, dy):
+    """Gradients of ``sum(hyperedge(adj, emb) * dy)`` w.r.t. ``adj`` and ``emb`` (float64)."""
+    a, e, g = (np.asarray(v, dtype=np.float64) for v in (adj, emb, dy))
+    t, dt = a.T @ e, a.T @ g
+    return (g @ t.T + e @ dt.T).astype(np.float32), (a @ dt).astype(np.float32)
+
+
 def hccf_forward(csr, params, n_layers, n_users):
     """``HCCFEncoder.forward`` (model/graph/HCCF.py:173-191) with keep_rate = 1 and dropout off."""
     ue, ie = params["embedding_dict.user_emb"], params["embedding_dict.item_emb"]
@@ -239,9 +253,7 @@ def hccf_forward(csr, params, n_layers, n_users):
     hi = (ie.astype(np.float64) @ params["embedding_dict.item_w"].astype(np.float64)).astype(np.float32)
     gcn_h, hyp_h = [], []
 
-    def hgnn(adj, emb):  # HGNNLayer.forward, HCCF.py:206-211
-        a = adj.astype(np.float64)
-        return (a @ (a.T @ emb.astype(np.float64))).astype(np.float32)
+    hgnn = hyperedge
 
     for _ in range(n_layers):
         gcn = spmm(*csr, hidden[-1])

@@ -255,6 +255,31 @@ def test_hccf_encoder_matches_reference(hgr, golden, data):
 
 
 # ------------------------------------------------------------------------------------ scatter-mean form
+@pytest.mark.parametrize("n,k,d", [(1, 32, 32), (63, 64, 64), (3001, 128, 64), (30011, 128, 64), (4097, 256, 128), (2500, 32, 128)])
+def test_hyperedge_products_forward_backward(hgr, n, k, d):
+    """HGNNLayer.forward on the tall-and-skinny kernels (csrc/hyperedge.cu) against the float64 oracle: forward, both
+    gradients, ragged row counts (not a multiple of the 32-row staging tile or the 64-row output tile)."""
+    rng = np.random.default_rng(n + k + d)
+    h = (rng.standard_normal((n, k)) * 0.3).astype(np.float32)
+    e = rng.standard_normal((n, d)).astype(np.float32)
+    g = rng.standard_normal((n, d)).astype(np.float32)
+    ht, et = cuda(h).requires_grad_(True), cuda(e).requires_grad_(True)
+    assert hgr.ops.hyperedge_supported(ht, et)
+    y = hgr.ops.hyperedge(ht, et)
+    assert rel_err(y, O.hyperedge(h, e)) < RTOL  # 1e-5 relative (north_star), fp32 sums in a different order
+    (y * cuda(g)).sum().backward()
+    dh, de = O.hyperedge_grads(h, e, g)
+    assert rel_err(ht.grad, dh) < RTOL and rel_err(et.grad, de) < RTOL
+    y2 = hgr.ops.hyperedge(ht.detach(), et.detach())
+    assert np.array_equal(bits(y2), bits(y))  # partials are added in block order: reproducible
+    t = hgr.ops.tall_skinny_tn(cuda(h), cuda(e))
+    assert rel_err(t, h.astype(np.float64).T @ e.astype(np.float64)) < RTOL
+    with pytest.raises(ValueError):
+        hgr.ops.hyperedge(torch.ones(8, 48, device="cuda"), torch.ones(8, 64, device="cuda"))  # unsupported width fails loudly
+    with pytest.raises(hgr.lib.HgrError):
+        hgr.ops.tall_skinny_tn(torch.ones(8, 48, device="cuda"), torch.ones(8, 64, device="cuda"))
+
+
 def test_scatter_mean_form_matches_reference_golden_and_oracle(hgr, golden):
     from hypergraph_diffusion_for_recommendation_b200 import graph
 
