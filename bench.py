@@ -410,8 +410,12 @@ def run_ours(args):
     alg = spmm_algorithmic_bytes(n_rows, n_cols, nnz, D)
     avg_ms = sum(spmm_ms) / max(len(spmm_ms), 1)
     achieved = alg / (avg_ms * 1e-3) / 1e9 if spmm_ms else None
+    traffic = SPMM_DRAM_TRAFFIC.get((args.workload, world))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": SPMM_DRAM_TRAFFIC.get((args.workload, world)), "kernel": "spmm_rows_async_kernel<16,4,5> (+ spmm_heavy_reduce_kernel)", "launch_ms": avg_ms,
+                "traffic": traffic,
+                # the same launch time against the bytes that really crossed the HBM interface (ncu capture of this kernel and shape)
+                "dram_gbs": traffic / (avg_ms * 1e-3) / 1e9 if traffic and spmm_ms else None,
+                "dram_frac": traffic / (avg_ms * 1e-3) / 1e9 / peak if traffic and spmm_ms else None, "kernel": "spmm_rows_async_kernel<16,4,5> (+ spmm_heavy_reduce_kernel)", "launch_ms": avg_ms,
                 "launches_timed": len(spmm_ms), "algorithmic_bytes": alg, "peak_source": peak_src,
                 "spmm_share_of_step": ((2 * len(spmm_ms) / 3 * avg_ms) / ms_per_step if graphed is not None else sum(spmm_ms) / total_ms) if spmm_ms else None,
                 "note": "algorithmic bytes charge one 256-B row per nonzero to HBM (SURVEY.md 8d); the power-law graph lets L2 absorb "
