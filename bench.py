@@ -376,6 +376,7 @@ def run_ours(args):
         clocks.start()
     if world > 1:
         adj.n_fused = adj.n_collective = adj.n_published = 0
+        adj.phase_events = []
     total_ms, losses, launches = timed("device")
     clock_info = clocks.stop()
     exchange = None
@@ -383,6 +384,14 @@ def run_ours(args):
         # per step: propagations whose all-gather rode on the kernel epilogue (peer stores) vs NCCL collectives
         exchange = {"fused_gathers_per_step": adj.n_fused / (args.steps + args.warmup), "nccl_gathers_per_step": adj.n_collective / (args.steps + args.warmup),
                     "copy_kernel_gathers_per_step": adj.n_published / (args.steps + args.warmup), "fused": bool(adj.fused)}
+        # where the sharded step spends its time on this rank (CUDA events between the phases, timed steps only)
+        torch.cuda.synchronize()
+        phases = {}
+        for marks in adj.phase_events[args.warmup:]:
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1) / args.steps
+        exchange["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
+        adj.phase_events = None
     e2e_ms, _, _ = timed("e2e")
     eval_info = run_eval(model, eval_inputs, part, adj, world, rank, dev, barrier)
 

@@ -448,7 +448,17 @@ def train_step(model, optimizer, g: DistGraph, user_idx, pos_idx, neg_idx, reg: 
     """One sharded step of the reference's training loop (model/graph/LightGCN.py:49-66): propagate the owned
     rows, gather the final tables, fused BPR + L2 on the whole batch, backward, summed replicated gradients,
     optimiser step on the owned rows.  ``user_idx / pos_idx / neg_idx`` are GLOBAL dense ids."""
+    marks = []
+
+    def mark(name):  # bench: CUDA events between the phases of the step (g.phase_events = [] switches it on)
+        if getattr(g, "phase_events", None) is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    mark("start")
     out_u, out_i = model()[:2]
+    mark("encoder forward")
     own = _unsplit(out_u, out_i)
     part = g.part
     pu, pp, pn = part.perm_user(user_idx), part.perm_item(pos_idx), part.perm_item(neg_idx)
@@ -461,11 +471,17 @@ def train_step(model, optimizer, g: DistGraph, user_idx, pos_idx, neg_idx, reg: 
     else:
         full = g.gather_tables(own)
         rec_loss, reg_loss = loss_fn(full, full, pu, pp, pn, reg, batch_size)
+    mark("loss forward")
     optimizer.zero_grad(set_to_none=True)
     (rec_loss + reg_loss).backward()
+    mark("backward")
     if g.world > 1:
         sync_replicated_grads(model, group=g.group)
+    mark("replicated-gradient all_reduce")
     optimizer.step()
+    mark("optimizer")
+    if marks:
+        g.phase_events.append(marks)
     return torch.stack([rec_loss.detach(), reg_loss.detach()])
 
 
