@@ -277,7 +277,7 @@ def run_ours(args):
         model.train()  # HCCF.train calls model.train() every batch (HCCF.py:81): dropout on the learned incidence stays on
     else:
         model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
-    use_graph = world == 1 and args.model != "hccf" and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and small))
+    use_graph = world == 1 and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and small))
     optimizer = torch.optim.Adam(model.parameters(), lr=LR, fused=True, capturable=use_graph)
 
     # triples: the device sampler (csrc/sampler.cu: shuffled positives + rejection-sampled negatives, the body of
@@ -316,7 +316,12 @@ def run_ours(args):
     if use_graph:
         # warm up and capture with adam steps that count: restore parameters / optimizer state afterwards so that the timed
         # steps start from the same state as the ungraphed path
-        graphed = trainer.GraphedTrainStep(model, optimizer, REG, B, b_local)
+        if args.model == "hccf":
+            # torch.unique's variable-length result is replaced by the fixed-size sorted-with-gaps form (loss_torch.unique_padded)
+            graphed = trainer.GraphedStep(lambda tu, tp, tn: trainer.train_step_hccf(model, optimizer, tu, tp, tn, HCCF_TEMP, HCCF_SS_RATE,
+                                                                                     HCCF_KEEP, static_shapes=True), b_local, dev)
+        else:
+            graphed = trainer.GraphedTrainStep(model, optimizer, REG, B, b_local)
 
     def step(tri):
         if graphed is not None:

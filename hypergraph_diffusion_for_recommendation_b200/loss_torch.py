@@ -169,6 +169,22 @@ def contrastLoss(embeds1, embeds2, nodes, temp):
     return _SslLoss.apply(embeds1, embeds2, nodes, temp, 0, 1)
 
 
+def unique_padded(idx: torch.Tensor) -> torch.Tensor:
+    """``torch.unique(idx)`` at a FIXED size: the ids sorted ascending with every repeat replaced by -1 (an inactive slot of
+    ``contrastLoss``).  No host synchronisation and no data-dependent shape, so a training step that uses it can be captured
+    in a CUDA graph; the active entries stand in ``torch.unique``'s order."""
+    s = torch.sort(idx.reshape(-1)).values
+    first = torch.ones_like(s, dtype=torch.bool)
+    first[1:] = s[1:] != s[:-1]
+    return torch.where(first, s, torch.full_like(s, -1))
+
+
+def contrastLoss_padded(embeds1, embeds2, batch_idx, temp):
+    """``contrastLoss(embeds1, embeds2, torch.unique(batch_idx), temp)`` (the call of HCCF.calcLosses, model/graph/HCCF.py:62-66)
+    without the variable-length ``unique``: same loss and gradients to rounding."""
+    return _SslLoss.apply(embeds1, embeds2, unique_padded(batch_idx), temp, 0, 1)
+
+
 def InfoNCE(view1, view2, temperature, b_cos=True):
     """util/loss_torch.py:32-40."""
     return _SslLoss.apply(view1, view2, None, temperature, 1, 1 if b_cos else 0)

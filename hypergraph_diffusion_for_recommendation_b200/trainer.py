@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from .loss_torch import bpr_l2_from_tables, contrastLoss
+from .loss_torch import bpr_l2_from_tables, contrastLoss, unique_padded
 
 
 def train_step(model, optimizer, user_idx, pos_idx, neg_idx, reg: float, batch_size: int, forward=None):
@@ -23,15 +23,17 @@ def train_step(model, optimizer, user_idx, pos_idx, neg_idx, reg: float, batch_s
     return torch.stack([rec_loss.detach(), reg_loss.detach()])
 
 
-def train_step_hccf(model, optimizer, user_idx, pos_idx, neg_idx, temp: float, ss_rate: float, keep_rate: float, device_rng: bool = True):
+def train_step_hccf(model, optimizer, user_idx, pos_idx, neg_idx, temp: float, ss_rate: float, keep_rate: float, device_rng: bool = True,
+                    static_shapes: bool = False):
     """Per-batch body of ``HCCF.train`` (model/graph/HCCF.py:79-95) with ``calcLosses`` (:59-68): edge-dropped GCN +
     learned-hyperedge propagation, BPR, and per layer ``contrastLoss`` between the detached GCN view and the hypergraph
     view for users and items.  SSL nodes = the batch's unique user / positive-item ids (see oracle/torch_path.py).
-    ``device_rng``: draw the edge-drop mask on the GPU instead of the reference's CPU ``torch.rand(nnz)``."""
+    ``device_rng``: draw the edge-drop mask on the GPU instead of the reference's CPU ``torch.rand(nnz)``.
+    ``static_shapes``: ``loss_torch.unique_padded`` instead of ``torch.unique`` (no host sync, fixed shapes: capturable)."""
     n_users = model.data.n_users
     user_emb, item_emb, gcn_l, hyp_l = model(keep_rate=keep_rate, device_rng=device_rng)
     rec_loss, _ = bpr_l2_from_tables(user_emb, item_emb, user_idx, pos_idx, neg_idx, 0.0, 1.0)
-    un, pn = torch.unique(user_idx), torch.unique(pos_idx)
+    un, pn = (unique_padded(user_idx), unique_padded(pos_idx)) if static_shapes else (torch.unique(user_idx), torch.unique(pos_idx))
     ssl = 0
     for g, h in zip(gcn_l, hyp_l):
         g = g.detach()
@@ -43,32 +45,27 @@ def train_step_hccf(model, optimizer, user_idx, pos_idx, neg_idx, temp: float, s
     return torch.stack([rec_loss.detach(), ssl.detach()])
 
 
-class GraphedTrainStep:
-    """``train_step`` captured once into a CUDA graph and replayed: for graphs whose propagation takes tens of microseconds
-    (the L2-resident BASELINE shapes) the step is bound by ~25-60 kernel launches and the Python between them, not by the
-    kernels.  The batch's index tensors are copied into static buffers, the whole forward / loss / backward / Adam sequence
-    replays as one launch.  Requires a fixed batch size (the short last batch of an epoch runs through ``train_step``) and an
-    optimizer built with ``capturable=True``."""
+class GraphedStep:
+    """Any fixed-shape step ``fn(user_idx, pos_idx, neg_idx) -> losses`` captured into a CUDA graph (see GraphedTrainStep)."""
 
-    def __init__(self, model, optimizer, reg: float, batch_size: int, batch: int, forward=None, warmup: int = 3):
-        dev = next(model.parameters()).device
-        self.u = torch.zeros(batch, dtype=torch.int64, device=dev)
-        self.p = torch.zeros(batch, dtype=torch.int64, device=dev)
-        self.n = torch.zeros(batch, dtype=torch.int64, device=dev)
+    def __init__(self, fn, batch: int, device, warmup: int = 3):
+        self.u = torch.zeros(batch, dtype=torch.int64, device=device)
+        self.p = torch.zeros(batch, dtype=torch.int64, device=device)
+        self.n = torch.zeros(batch, dtype=torch.int64, device=device)
         self.batch = batch
-        side = torch.cuda.Stream(device=dev)
+        side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up off the default stream: lazy initialisation must not land in the capture
+        with torch.cuda.stream(side):
             for _ in range(warmup):
-                train_step(model, optimizer, self.u, self.p, self.n, reg, batch_size, forward)
+                fn(self.u, self.p, self.n)
         torch.cuda.current_stream().wait_stream(side)
         from . import _lib
 
         before = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.losses = train_step(model, optimizer, self.u, self.p, self.n, reg, batch_size, forward)
-        self.kernels_per_replay = _lib.launch_count() - before  # libhgr kernels inside one replay
+            self.losses = fn(self.u, self.p, self.n)
+        self.kernels_per_replay = _lib.launch_count() - before
 
     def __call__(self, user_idx, pos_idx, neg_idx):
         if user_idx.numel() != self.batch:
@@ -78,3 +75,15 @@ class GraphedTrainStep:
         self.n.copy_(neg_idx, non_blocking=True)
         self.graph.replay()
         return self.losses
+
+
+class GraphedTrainStep(GraphedStep):
+    """``train_step`` captured once into a CUDA graph and replayed: for graphs whose propagation takes tens of microseconds
+    (the L2-resident BASELINE shapes) the step is bound by ~25-60 kernel launches and the Python between them, not by the
+    kernels.  The batch's index tensors are copied into static buffers, the whole forward / loss / backward / Adam sequence
+    replays as one launch.  Requires a fixed batch size (the short last batch of an epoch runs through ``train_step``) and an
+    optimizer built with ``capturable=True``."""
+
+    def __init__(self, model, optimizer, reg: float, batch_size: int, batch: int, forward=None, warmup: int = 3):
+        super().__init__(lambda u, p, n: train_step(model, optimizer, u, p, n, reg, batch_size, forward), batch,
+                         next(model.parameters()).device, warmup)

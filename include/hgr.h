@@ -277,8 +277,10 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
  * (always on for kind 0, b_cos for kind 1).  loss: device float[1].  `saved` (hgr_ssl_workspace_bytes(M, D), 256-byte
  * aligned) carries the normalised rows, row sums and coefficients to the backward call.  The [M, M] logits are never
  * materialised.  Backward: dE1 / dE2 ([n_rows, D], zero-filled by the caller; either may be NULL for a detached
- * operand) receive grad_out[0] * d loss / d E at the picked rows.  Out-of-range nodes are counted in
- * *bad_index_count (device int, caller zeroes) and contribute zero rows.
+ * operand) receive grad_out[0] * d loss / d E at the picked rows.  A NEGATIVE entry of nodes is an inactive slot: it
+ * takes no part in the loss (no row, no column, not counted in the mean), which lets a fixed-size batch stand in for
+ * torch.unique's variable-length result (sorted ids with the repeats replaced by -1: CUDA-graph capturable).  Entries
+ * beyond the tables are counted in *bad_index_count (device int, caller zeroes) and skipped the same way.
  * ------------------------------------------------------------------------------------------- */
 size_t hgr_ssl_workspace_bytes(int64_t M, int32_t D);
 int hgr_ssl_loss_fwd_f32(const float *E1, const float *E2, int64_t n_rows1, int64_t n_rows2, int32_t D, const int64_t *nodes,

@@ -127,3 +127,77 @@ def test_infonce_against_torch_expression(L, b_cos):
     if b_cos:
         o_loss, o_d1, o_d2 = O.info_nce(v1, v2, 0.2)
         assert rel_err(loss, o_loss) < RTOL and rel_err(t1.grad, o_d1) < 5e-5
+
+
+@pytest.mark.parametrize("batch,n_rows", [(1, 50), (700, 300), (4096, 3000)])
+def test_contrast_loss_padded_batch_equals_unique(L, batch, n_rows):
+    """``contrastLoss_padded(e1, e2, batch_ids)`` -- the fixed-shape, CUDA-graph-capturable form (sorted ids, repeats replaced
+    by inactive slots) -- against ``contrastLoss(e1, e2, torch.unique(batch_ids))`` and the oracle: loss and both gradients."""
+    rng = np.random.default_rng(batch)
+    e1 = rng.standard_normal((n_rows, 64)).astype(np.float32) * 0.3
+    e2 = rng.standard_normal((n_rows, 64)).astype(np.float32) * 0.3
+    ids = rng.integers(0, n_rows, batch)  # with repeats
+    t_ids = torch.from_numpy(ids).cuda()
+    pad = L.unique_padded(t_ids)
+    uniq = np.unique(ids)
+    assert pad.shape == t_ids.shape and np.array_equal(pad[pad >= 0].cpu().numpy(), uniq)  # torch.unique's order, gaps marked -1
+    a1, a2 = torch.from_numpy(e1).cuda().requires_grad_(True), torch.from_numpy(e2).cuda().requires_grad_(True)
+    b1, b2 = torch.from_numpy(e1).cuda().requires_grad_(True), torch.from_numpy(e2).cuda().requires_grad_(True)
+    lp = L.contrastLoss_padded(a1, a2, t_ids, 0.2)
+    lu = L.contrastLoss(b1, b2, torch.unique(t_ids), 0.2)
+    (2.0 * lp).backward()
+    (2.0 * lu).backward()
+    if uniq.size == 1:
+        assert abs(float(lp) - float(lu)) < 1e-6
+        return
+    assert rel_err(lp, lu) < 1e-6  # same terms, tiles cut differently
+    assert rel_err(a1.grad, b1.grad) < 1e-5 and rel_err(a2.grad, b2.grad) < 1e-5
+    o_loss, o_d1, o_d2 = O.contrast_loss(e1, e2, uniq, 0.2)
+    assert rel_err(lp, o_loss) < RTOL and rel_err(a1.grad, 2.0 * o_d1) < 5e-5 and rel_err(a2.grad, 2.0 * o_d2) < 5e-5
+    touched = np.zeros(n_rows, dtype=bool)
+    touched[uniq] = True
+    assert not a1.grad[torch.from_numpy(~touched).cuda()].any()  # rows outside the batch get no gradient
+
+
+def test_hccf_step_replays_as_a_cuda_graph():
+    """The HCCF step with ``static_shapes=True`` captured once and replayed: losses equal to the eager step on the same
+    batch and random streams are finite and move the parameters (no torch.unique, no host sync inside the step)."""
+    from hypergraph_diffusion_for_recommendation_b200 import encoders, graph, trainer
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions
+
+    g = powerlaw_interactions(400, 600, 9000, seed=2)
+    dev = torch.device("cuda")
+    u, i = torch.from_numpy(g.train_u).to(dev), torch.from_numpy(g.train_i).to(dev)
+    data = type("D", (), {})()
+    data.n_users, data.n_items = 400, 600
+    data.norm_adj = graph.build_norm_adj(u, i, 400, 600, device=dev)
+    conf = {"lrate": 0.001, "lr_decay": 1.0, "max_epoch": 1, "batch_size": 512, "reg": 0.0, "embedding_size": 64, "hyper_dim": 128,
+            "drop_rate": 0.0, "p": 0.5, "n_layers": 2}
+    torch.manual_seed(5)
+    model = encoders.HCCFEncoder(conf, data).to(dev)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=0.001, fused=True, capturable=True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    pick = torch.randint(0, u.numel(), (512,), device=dev, generator=gen)
+    tu, tp, tn = u[pick].long(), i[pick].long(), torch.randint(0, 600, (512,), device=dev, generator=gen)
+    # keep_rate 1 / drop_rate 0: no random stream inside the step, so eager and replayed losses can be compared
+    eager = trainer.train_step_hccf(model, opt, tu, tp, tn, 0.2, 0.1, 1.0, static_shapes=False).clone()
+    torch.manual_seed(5)
+    model2 = encoders.HCCFEncoder(conf, data).to(dev)
+    model2.train()
+    opt2 = torch.optim.Adam(model2.parameters(), lr=0.001, fused=True, capturable=True)
+    before = {k: v.detach().clone() for k, v in model2.state_dict().items()}
+    step = trainer.GraphedStep(lambda a, b, c: trainer.train_step_hccf(model2, opt2, a, b, c, 0.2, 0.1, 1.0, static_shapes=True), 512, dev,
+                               warmup=1)
+    # the warm-up step ran on zero indices: put parameters and Adam state back IN PLACE (the graph holds their addresses)
+    model2.load_state_dict(before)
+    for st in opt2.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    out = step(tu, tp, tn).clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and step.kernels_per_replay > 20
+    assert rel_err(out, eager) < 1e-5
+    assert (model2.embedding_dict["user_emb"] - before["embedding_dict.user_emb"]).abs().max() > 0
