@@ -78,9 +78,16 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float *__restric
                                                           float *__restrict__ T) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_elems) return;
-    float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * n_elems + e];
-    T[e] = s;
+    // eight independent chains (blocks b = c mod 8) keep eight loads in flight instead of one dependent load per partial,
+    // then a fixed combine: still one order, whatever the launch
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int b = 0;
+    for (; b + 8 <= n_blocks; b += 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s[c] += partials[(size_t)(b + c) * n_elems + e];
+    }
+    for (int c = 0; b < n_blocks; ++b, ++c) s[c] += partials[(size_t)b * n_elems + e];
+    T[e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
 // Y[n, N] = [A1 | A2] B with B [(K1 + K2), N] resident in shared memory.  Block = 64-row tile; thread = 4 output columns

@@ -414,6 +414,14 @@ class HGNNLayer(nn.Module):
         return torch.mm(adj, torch.mm(adj.T, embeds))
 
 
+def _dense_incidence(emb, w):
+    """``emb @ w`` (HCCF.py:178-179): tall-and-skinny in the forward pass, and its weight gradient ``emb.T @ dH`` contracts
+    over all nodes -- libhgr kernels where the widths allow, the library GEMM otherwise."""
+    if ops.tall_times_small_supported(emb, w):
+        return ops.tall_times_small(emb, w)
+    return emb @ w
+
+
 class HCCFEncoder(nn.Module):
     def __init__(self, conf, data):
         super(HCCFEncoder, self).__init__()
@@ -457,8 +465,8 @@ class HCCFEncoder(nn.Module):
         hidden = [embeddings]
         gcn_hidden = []
         hgnn_hidden = []
-        hyper_uu = self.embedding_dict['user_emb'] @ self.embedding_dict['user_w']
-        hyper_ii = self.embedding_dict['item_emb'] @ self.embedding_dict['item_w']
+        hyper_uu = _dense_incidence(self.embedding_dict['user_emb'], self.embedding_dict['user_w'])
+        hyper_ii = _dense_incidence(self.embedding_dict['item_emb'], self.embedding_dict['item_w'])
         for i in range(self.n_layers):
             rand = torch.rand(self.sparse_norm_adj._nnz(), device=self.sparse_norm_adj.device) if device_rng and keep_rate != 1.0 else None
             gcn_emb = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate, rand), hidden[-1])

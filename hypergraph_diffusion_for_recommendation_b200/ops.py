@@ -343,3 +343,34 @@ def hyperedge(h: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
     if not hyperedge_supported(h, e):
         raise ValueError("hyperedge: need float32 CUDA h [n, 32|64|128|256] and e [n, 32|64|128], got %s and %s" % (tuple(h.shape), tuple(e.shape)))
     return _Hyperedge.apply(h, e)
+
+
+class _TallTimesSmall(torch.autograd.Function):
+    """``x @ w`` for a tall ``x [n, K]`` and a small ``w [K, N]`` (HCCF's ``hyper = E0 @ W``, model/graph/HCCF.py:178-179):
+    forward ``rows_times_small``, backward ``dx = dy @ w.T`` (same kernel) and ``dw = x.T @ dy`` (the tall-skinny reduce)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.contiguous(), w.contiguous()
+        ctx.save_for_backward(x, w)
+        return rows_times_small(x, None, w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = rows_times_small(dy, None, w.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dw = tall_skinny_tn(x, dy) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def tall_times_small_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
+    return (x.is_cuda and w.is_cuda and x.dtype == w.dtype == torch.float32 and x.dim() == w.dim() == 2 and x.shape[1] == w.shape[0]
+            and x.shape[1] in (32, 64, 128) and w.shape[1] in (32, 64, 128))
+
+
+def tall_times_small(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``x @ w`` on libhgr for ``x [n, 32|64|128]`` and ``w`` of width 32 | 64 | 128; anything else raises."""
+    if not tall_times_small_supported(x, w):
+        raise ValueError("tall_times_small: unsupported shapes %s @ %s" % (tuple(x.shape), tuple(w.shape)))
+    return _TallTimesSmall.apply(x, w)

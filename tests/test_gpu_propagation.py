@@ -280,6 +280,23 @@ def test_hyperedge_products_forward_backward(hgr, n, k, d):
         hgr.ops.tall_skinny_tn(torch.ones(8, 48, device="cuda"), torch.ones(8, 64, device="cuda"))
 
 
+@pytest.mark.parametrize("n,k,w", [(5, 64, 128), (3001, 64, 128), (20000, 32, 64), (777, 128, 32)])
+def test_tall_times_small_forward_backward(hgr, n, k, w):
+    """HCCF's ``hyper = E0 @ W`` (HCCF.py:178-179) on the libhgr kernels against float64: output, dE0 and the tall-skinny dW."""
+    rng = np.random.default_rng(n + w)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    m = (rng.standard_normal((k, w)) * 0.2).astype(np.float32)
+    g = rng.standard_normal((n, w)).astype(np.float32)
+    xt, mt = cuda(x).requires_grad_(True), cuda(m).requires_grad_(True)
+    y = hgr.ops.tall_times_small(xt, mt)
+    (y * cuda(g)).sum().backward()
+    x64, m64, g64 = x.astype(np.float64), m.astype(np.float64), g.astype(np.float64)
+    assert rel_err(y, x64 @ m64) < RTOL
+    assert rel_err(xt.grad, g64 @ m64.T) < RTOL and rel_err(mt.grad, x64.T @ g64) < RTOL
+    with pytest.raises(ValueError):
+        hgr.ops.tall_times_small(torch.ones(8, 48, device="cuda"), torch.ones(48, 64, device="cuda"))
+
+
 def test_scatter_mean_form_matches_reference_golden_and_oracle(hgr, golden):
     from hypergraph_diffusion_for_recommendation_b200 import graph
 
