@@ -289,9 +289,12 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_async_kernel(hgr_csr
     finish_row<LPR>(acc, row, gl, gmask, ep, Y);
 }
 
-// One block per split row: group g adds the partial rows of chunks g, g + GPB, ... in order, group 0 then adds the GPB
-// group sums in group order and runs the epilogue.  A fixed order (deterministic), and the most popular item's ~1 200
-// chunks are no longer walked by a single group.
+// Sums the partial rows of the split rows and runs the epilogue.  A block takes GPB consecutive split rows.  Most of them
+// have a handful of chunks (a power-law tail cut at chunk_nnz): ONE group adds those in chunk order.  A row with more than
+// GPB chunks is then reduced by the whole block: group g adds chunks g, g + GPB, ... in order, group 0 adds the GPB group
+// sums in group order (for <= GPB chunks the two orders are the same chain, so the split point never changes a bit).
+// A fixed order either way: deterministic.  The first version launched one block per split row - 22 000 blocks of which
+// all but a few hundred used 1/16 of their threads (0.14 ms per propagation).
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A, const float4 *__restrict__ partials,
                                                                      float *__restrict__ Y, hgr_epilogue_t ep) {
@@ -300,34 +303,64 @@ __global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A
     const int gl = threadIdx.x % LPR;
     const int g = threadIdx.x / LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
-    const int h = blockIdx.x;
-    const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = c0 + g; c < c1; c += (int64_t)GPB * kUnroll) {
-        float4 p[kUnroll];
+    const int h0 = blockIdx.x * GPB;
+    const int h_end = h0 + GPB < A.n_heavy_rows ? h0 + GPB : A.n_heavy_rows;
+    {
+        const int h = h0 + g;
+        if (h < h_end) {
+            const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
+            if (c1 - c0 <= GPB) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int64_t c = c0; c < c1; c += 4) {  // four loads in flight, added in chunk order
+                    float4 p[4];
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k)
-            if (c + (int64_t)k * GPB < c1) p[k] = ld_stream_f4(partials + (c + (int64_t)k * GPB) * LPR + gl);
+                    for (int k = 0; k < 4; ++k)
+                        if (c + k < c1) p[k] = ld_stream_f4(partials + (c + k) * LPR + gl);
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k)
-            if (c + (int64_t)k * GPB < c1) {
-                acc.x += p[k].x;
-                acc.y += p[k].y;
-                acc.z += p[k].z;
-                acc.w += p[k].w;
+                    for (int k = 0; k < 4; ++k)
+                        if (c + k < c1) {
+                            acc.x += p[k].x;
+                            acc.y += p[k].y;
+                            acc.z += p[k].z;
+                            acc.w += p[k].w;
+                        }
+                }
+                finish_row<LPR>(acc, A.heavy_rows[h], gl, gmask, ep, Y);
             }
+        }
     }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    if (g != 0) return;
-    for (int k = 1; k < GPB; ++k) {
-        const float4 q = sh[k * LPR + gl];
-        acc.x += q.x;
-        acc.y += q.y;
-        acc.z += q.z;
-        acc.w += q.w;
+    for (int h = h0; h < h_end; ++h) {  // block-uniform loop: the rows with more chunks than groups
+        const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
+        if (c1 - c0 <= GPB) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t c = c0 + g; c < c1; c += (int64_t)GPB * kUnroll) {
+            float4 p[kUnroll];
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k)
+                if (c + (int64_t)k * GPB < c1) p[k] = ld_stream_f4(partials + (c + (int64_t)k * GPB) * LPR + gl);
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k)
+                if (c + (int64_t)k * GPB < c1) {
+                    acc.x += p[k].x;
+                    acc.y += p[k].y;
+                    acc.z += p[k].z;
+                    acc.w += p[k].w;
+                }
+        }
+        __syncthreads();  // sh is free again
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        if (g == 0) {
+            for (int k = 1; k < GPB; ++k) {
+                const float4 q = sh[k * LPR + gl];
+                acc.x += q.x;
+                acc.y += q.y;
+                acc.z += q.z;
+                acc.w += q.w;
+            }
+            finish_row<LPR>(acc, A.heavy_rows[h], gl, gmask, ep, Y);
+        }
     }
-    finish_row<LPR>(acc, A.heavy_rows[h], gl, gmask, ep, Y);
 }
 
 static int check_csr(const hgr_csr_t *A, const char *name) {
@@ -369,7 +402,7 @@ static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_e
                                                                           reinterpret_cast<float4 *>(ws), (int)heavy_blocks);
     HGR_LAUNCH_OK("spmm_rows_kernel");
     if (A.n_heavy_rows > 0) {
-        spmm_heavy_reduce_kernel<LPR><<<(unsigned)A.n_heavy_rows, kThreads, 0, st>>>(
+        spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, kThreads / LPR), kThreads, 0, st>>>(
             A, reinterpret_cast<const float4 *>(ws), Y, ep);
         HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
     }
@@ -390,7 +423,7 @@ static int launch_spmm_async(const hgr_csr_t &A, const float *X, float *Y, const
                                                                                  partials, (int)heavy_blocks);
     HGR_LAUNCH_OK("spmm_rows_async_kernel");
     if (A.n_heavy_rows > 0) {
-        spmm_heavy_reduce_kernel<LPR><<<(unsigned)A.n_heavy_rows, kThreads, 0, st>>>(A, partials, Y, ep);
+        spmm_heavy_reduce_kernel<LPR><<<(unsigned)ceil_div(A.n_heavy_rows, kThreads / LPR), kThreads, 0, st>>>(A, partials, Y, ep);
         HGR_LAUNCH_OK("spmm_heavy_reduce_kernel");
     }
     return HGR_OK;
