@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--world", type=int, default=8)
     ap.add_argument("--rank", type=int, default=0)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--variants", default="0", help="hgr_set_spmm_variant values to time (include/hgr.h)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     U, I, E = 1_250_000 * args.world, 250_000 * args.world, 125_000_000 * args.world
@@ -37,20 +38,25 @@ def main():
     print("block %d of %d: rows %d cols %d nnz %d, heavy rows %d, built in %.1f s" % (
         args.rank, args.world, part.n_loc, part.n_glob, block._nnz(), block.desc.n_heavy_rows, time.time() - t0), flush=True)
     x = torch.randn(part.n_glob, 64, device=dev)
-    for _ in range(2):
-        y = ops.spmm_raw(block, x)
-    ts = []
-    for _ in range(args.iters):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        y = ops.spmm_raw(block, x)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = sorted(ts)[len(ts) // 2]
-    nnz = block._nnz()
-    alg = 8 * (part.n_loc + 1) + 8 * nnz + 256 * nnz + 256 * part.n_loc
-    print("spmm median %.3f ms | %.1f Gnnz/s | algorithmic %.1f GB -> %.0f GB/s" % (ms, nnz / ms / 1e6, alg / 1e9, alg / ms / 1e6), flush=True)
+    from hypergraph_diffusion_for_recommendation_b200 import _lib
+
+    for variant in (int(v) for v in args.variants.split(",")):
+        _lib.check(_lib.lib().hgr_set_spmm_variant(variant))
+        print("variant %d" % variant, flush=True)
+        for _ in range(2):
+            y = ops.spmm_raw(block, x)
+        ts = []
+        for _ in range(args.iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            y = ops.spmm_raw(block, x)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        nnz = block._nnz()
+        alg = 8 * (part.n_loc + 1) + 8 * nnz + 256 * nnz + 256 * part.n_loc
+        print("spmm median %.3f ms | %.1f Gnnz/s | algorithmic %.1f GB -> %.0f GB/s" % (ms, nnz / ms / 1e6, alg / 1e9, alg / ms / 1e6), flush=True)
 
 
 if __name__ == "__main__":
