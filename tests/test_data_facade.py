@@ -104,9 +104,11 @@ def test_interaction_against_the_loop_restatement_on_random_lists():
     rng = np.random.default_rng(5)
     for trial in range(4):
         n = 4000
-        tr = [[int(u), int(i), float(r)] for u, i, r in zip(rng.integers(0, 300, n) * 7 + 3, rng.integers(0, 500, n) * 3 + 11,
+        # the last trial uses raw ids spread over 2^52: the packed-key sort does not fit and the np.unique path runs
+        su, si = (1 << 52) // 300 if trial == 3 else 7, (1 << 52) // 600 if trial == 3 else 3
+        tr = [[int(u), int(i), float(r)] for u, i, r in zip(rng.integers(0, 300, n) * su + 3, rng.integers(0, 500, n) * si + 11,
                                                             rng.choice([1.0, 1.0, 2.0, 0.5], n))]
-        te = [[int(u), int(i), float(r)] for u, i, r in zip(rng.integers(0, 330, 900) * 7 + 3, rng.integers(0, 600, 900) * 3 + 11,
+        te = [[int(u), int(i), float(r)] for u, i, r in zip(rng.integers(0, 330, 900) * su + 3, rng.integers(0, 600, 900) * si + 11,
                                                             rng.choice([1.0, 3.0], 900))]
         ref = O.generate_set(tr, te)
         d = D.Interaction(None, tr, te)
