@@ -233,26 +233,18 @@ __device__ __forceinline__ void ev_poison(uint32_t (&v)[32], int col0, int n_ite
     }
 }
 
-// Append the columns of one 4-column group that meet the user's threshold to the user's candidate list.
+// Append the columns of one 4-column group that meet the user's threshold to the user's candidate list.  Branch-free: the
+// four slots are computed up front and the stores are predicated, so a warp in which one lane appends one column does not
+// walk four reconvergence regions.
 __device__ __noinline__ int ev_append4(float x0, float x1, float x2, float x3, float thr, int col, int cnt, int cap,
                                        float2 *__restrict__ crow) {
-    if (x0 >= thr) {
-        if (cnt < cap) crow[cnt] = make_float2(x0, __int_as_float(col));
-        ++cnt;
-    }
-    if (x1 >= thr) {
-        if (cnt < cap) crow[cnt] = make_float2(x1, __int_as_float(col + 1));
-        ++cnt;
-    }
-    if (x2 >= thr) {
-        if (cnt < cap) crow[cnt] = make_float2(x2, __int_as_float(col + 2));
-        ++cnt;
-    }
-    if (x3 >= thr) {
-        if (cnt < cap) crow[cnt] = make_float2(x3, __int_as_float(col + 3));
-        ++cnt;
-    }
-    return cnt;
+    const bool h0 = x0 >= thr, h1 = x1 >= thr, h2 = x2 >= thr, h3 = x3 >= thr;
+    const int c0 = cnt, c1 = c0 + (h0 ? 1 : 0), c2 = c1 + (h1 ? 1 : 0), c3 = c2 + (h2 ? 1 : 0);
+    if (h0 && c0 < cap) crow[c0] = make_float2(x0, __int_as_float(col));
+    if (h1 && c1 < cap) crow[c1] = make_float2(x1, __int_as_float(col + 1));
+    if (h2 && c2 < cap) crow[c2] = make_float2(x2, __int_as_float(col + 2));
+    if (h3 && c3 < cap) crow[c3] = make_float2(x3, __int_as_float(col + 3));
+    return c3 + (h3 ? 1 : 0);
 }
 
 template <int MODE>
