@@ -96,7 +96,8 @@ template <int N>
 __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const float *__restrict__ A1, int K1,
                                                                       const float *__restrict__ A2, int K2,
                                                                       const float *__restrict__ B, int64_t n,
-                                                                      float *__restrict__ Y) {
+                                                                      float *__restrict__ Y, const float *__restrict__ bias,
+                                                                      int relu) {
     constexpr int TX = N / 4, TY = kHeThreads / TX, RPT = 64 / TY;  // rows per thread
     extern __shared__ __align__(16) float he_smem[];
     const int Kc = K1 + K2;
@@ -136,10 +137,14 @@ __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const floa
                 acc[i].z = fmaf(a.w, b[3].z, acc[i].z); acc[i].w = fmaf(a.w, b[3].w, acc[i].w);
             }
         }
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) bv = __ldg(reinterpret_cast<const float4 *>(bias) + tx);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const int64_t r = r0 + ty + TY * i;
-            if (r < n) reinterpret_cast<float4 *>(Y + r * N)[tx] = acc[i];
+            float4 o = make_float4(acc[i].x + bv.x, acc[i].y + bv.y, acc[i].z + bv.z, acc[i].w + bv.w);
+            if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            if (r < n) reinterpret_cast<float4 *>(Y + r * N)[tx] = o;
         }
     }
 }
@@ -208,7 +213,13 @@ int hgr_tall_skinny_tn_f32(const float *H, const float *E, int64_t n, int32_t K,
 
 int hgr_rows_times_small_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
                              float *Y, hgr_stream_t stream) {
+    return hgr_rows_times_small_bias_f32(A1, K1, A2, K2, B, N, n, Y, nullptr, 0, stream);
+}
+
+int hgr_rows_times_small_bias_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
+                                  float *Y, const float *bias, int32_t relu, hgr_stream_t stream) {
     using namespace hgr;
+    HGR_REQUIRE(aligned16(bias), "bias must be 16-byte aligned");
     HGR_REQUIRE(n >= 0, "n negative");
     HGR_REQUIRE(K1 > 0 && K1 % 4 == 0 && K2 >= 0 && K2 % 4 == 0 && K1 + K2 <= 256, "K1 = %d, K2 = %d unsupported", K1, K2);
     HGR_REQUIRE(small_dim_ok(N) || N == 256, "N = %d unsupported (32, 64, 128 or 256)", N);
@@ -224,7 +235,7 @@ int hgr_rows_times_small_f32(const float *A1, int32_t K1, const float *A2, int32
 #define HGR_RTS(NN)                                                                                                          \
     do {                                                                                                                     \
         HGR_CUDA_OK(cudaFuncSetAttribute(rows_times_small_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rows_times_small_kernel<NN><<<(unsigned)blocks, kHeThreads, smem, st>>>(A1, K1, A2, K2, B, n, Y);                     \
+        rows_times_small_kernel<NN><<<(unsigned)blocks, kHeThreads, smem, st>>>(A1, K1, A2, K2, B, n, Y, bias, relu);                     \
     } while (0)
     switch (N) {
         case 32: HGR_RTS(32); break;

@@ -228,8 +228,7 @@ class MLP(nn.Module):
     def forward(self, x):
         x = self._norm(self.normalizations[0], x)
         for i, lin in enumerate(self.lins[:-1]):
-            x = ops.linear(x, lin.weight, lin.bias)
-            x = F.relu(x, inplace=True)
+            x = ops.linear(x, lin.weight, lin.bias, relu=True)
             x = self._norm(self.normalizations[i + 1], x)
             x = F.dropout(x, p=self.dropout, training=self.training)
         return ops.linear(x, self.lins[-1].weight, self.lins[-1].bias)
@@ -344,7 +343,7 @@ class EquivSetGNN(nn.Module):
 
     def forward(self, x, sparse_norm_adj, n_nodes=None, ui_adj=None, act=True):
         x = self.dropout(x)
-        x = F.relu(ops.linear(x, self.lin_in.weight, self.lin_in.bias))
+        x = ops.linear(x, self.lin_in.weight, self.lin_in.bias, relu=True)
         x0 = x
         for i in range(self.nlayer):
             x = self.dropout(x)

@@ -299,13 +299,14 @@ def tall_skinny_tn(h: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def rows_times_small(a1: torch.Tensor, a2: torch.Tensor | None, b: torch.Tensor) -> torch.Tensor:
-    """``cat([a1, a2], 1) @ b`` for a small ``b`` kept in shared memory (hgr_rows_times_small_f32)."""
+def rows_times_small(a1: torch.Tensor, a2: torch.Tensor | None, b: torch.Tensor, bias: torch.Tensor | None = None,
+                     relu: bool = False) -> torch.Tensor:
+    """``[relu](cat([a1, a2], 1) @ b [+ bias])`` for a small ``b`` kept in shared memory (hgr_rows_times_small_bias_f32)."""
     n, k1 = a1.shape
     k2 = 0 if a2 is None else a2.shape[1]
     y = torch.empty((n, b.shape[1]), dtype=torch.float32, device=a1.device)
-    _lib.check(_lib.lib().hgr_rows_times_small_f32(a1.data_ptr(), k1, _lib.ptr(a2), k2, b.data_ptr(), b.shape[1], n, y.data_ptr(),
-                                                   _lib.stream_ptr()))
+    _lib.check(_lib.lib().hgr_rows_times_small_bias_f32(a1.data_ptr(), k1, _lib.ptr(a2), k2, b.data_ptr(), b.shape[1], n, y.data_ptr(),
+                                                        _lib.ptr(bias), 1 if relu else 0, _lib.stream_ptr()))
     return y
 
 
@@ -377,30 +378,36 @@ def tall_times_small(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 
 
 class _Linear(torch.autograd.Function):
-    """``F.linear(x, weight, bias)`` for tall inputs: forward and ``dx`` on the library GEMM, the weight gradient
-    ``dy.T @ x`` -- a contraction over ALL rows that cuBLAS runs as a few-block SIMT kernel (0.84 ms for 1.5 M rows of 64) -- on
-    the tall-skinny reduce of csrc/hyperedge.cu."""
+    """``[relu](F.linear(x, weight, bias))`` for tall inputs.  Forward: one pass of the rows x small-matrix kernel with the bias
+    (and the ReLU) in its epilogue, instead of cuBLAS sgemm + bias kernel + ReLU kernel (0.37 + 0.40 + 0.11 ms for 1.5 M rows of
+    64).  Backward: ``dx`` on the library GEMM, the weight gradient ``dy.T @ x`` -- a contraction over ALL rows that cuBLAS runs as
+    a few-block SIMT kernel (0.84 ms) -- on the tall-skinny reduce of csrc/hyperedge.cu."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+    def forward(ctx, x, weight, bias, relu):
+        x = x.contiguous()
+        y = rows_times_small(x, None, weight.t().contiguous(), None if bias is None else bias.contiguous(), relu)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.has_bias, ctx.relu = bias is not None, relu
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
         dy = dy.contiguous()
+        if ctx.relu:
+            dy = dy * (y > 0)
         dx = dy @ weight if ctx.needs_input_grad[0] else None
-        dw = tall_skinny_tn(dy, x.contiguous()) if ctx.needs_input_grad[1] else None
+        dw = tall_skinny_tn(dy, x) if ctx.needs_input_grad[1] else None
         db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
-    """Drop-in for ``nn.Linear.forward`` on ``[rows, in]`` float32 CUDA inputs whose widths the tall-skinny kernel covers
-    (out in {32, 64, 128, 256}, in in {32, 64, 128}); other shapes go through ``F.linear`` unchanged."""
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool = False) -> torch.Tensor:
+    """Drop-in for ``nn.Linear.forward`` (``relu=True``: followed by ``F.relu``) on ``[rows, in]`` float32 CUDA inputs whose
+    widths the libhgr kernels cover (out in {32, 64, 128, 256}, in in {32, 64, 128}); other shapes go through ``F.linear``."""
     if (x.is_cuda and x.dim() == 2 and x.dtype == weight.dtype == torch.float32 and weight.shape[0] in (32, 64, 128, 256)
-            and weight.shape[1] in (32, 64, 128) and x.shape[0] >= 4096 and torch.is_grad_enabled() and weight.requires_grad):
-        return _Linear.apply(x, weight, bias)
-    return torch.nn.functional.linear(x, weight, bias)
+            and weight.shape[1] in (32, 64, 128) and x.shape[0] >= 4096):
+        return _Linear.apply(x, weight, bias, relu)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return torch.relu(y) if relu else y

@@ -210,6 +210,11 @@ int hgr_tall_skinny_tn_f32(const float *H, const float *E, int64_t n, int32_t K,
                            size_t workspace_bytes, hgr_stream_t stream);
 int hgr_rows_times_small_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
                              float *Y, hgr_stream_t stream);
+/* The same product with the epilogue of a Linear layer: Y = [relu]([A1 | A2] . B + bias[N]) -- nn.Linear.forward (+ F.relu) of the
+ * MLP / LocalAwareEncoder input layers (model/layers/MLP.py:109-117, model/graph/HGNN_HD3.py:416) with B = weight^T, in one pass
+ * instead of cuBLAS sgemm + bias kernel + ReLU kernel.  bias may be NULL. */
+int hgr_rows_times_small_bias_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
+                                  float *Y, const float *bias, int32_t relu, hgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BPR + L2 loss fused with the embedding gathers (util/loss_torch.py:5-9,17-21 called from

@@ -297,6 +297,31 @@ def test_tall_times_small_forward_backward(hgr, n, k, w):
         hgr.ops.tall_times_small(torch.ones(8, 48, device="cuda"), torch.ones(48, 64, device="cuda"))
 
 
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("n,k,w", [(4096, 64, 64), (10001, 32, 128), (5000, 128, 64)])
+def test_linear_layer_kernel_matches_torch(hgr, n, k, w, relu):
+    """``ops.linear`` (nn.Linear.forward [+ ReLU] of the MLP / LocalAwareEncoder input layers on the rows x small-matrix kernel,
+    weight gradient on the tall-skinny reduce) against float64: output and all three gradients."""
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(n + w + relu)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    wt = (rng.standard_normal((w, k)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(w).astype(np.float32)
+    g = rng.standard_normal((n, w)).astype(np.float32)
+    xs, ws, bs = cuda(x).requires_grad_(True), cuda(wt).requires_grad_(True), cuda(b).requires_grad_(True)
+    y = hgr.ops.linear(xs, ws, bs, relu=relu)
+    (y * cuda(g)).sum().backward()
+    xr, wr, br = (torch.from_numpy(v).double().requires_grad_(True) for v in (x, wt, b))
+    yr = F.linear(xr, wr, br)
+    yr = torch.relu(yr) if relu else yr
+    (yr * torch.from_numpy(g).double()).sum().backward()
+    assert rel_err(y, yr.detach().numpy()) < RTOL
+    assert rel_err(xs.grad, xr.grad.numpy()) < RTOL and rel_err(ws.grad, wr.grad.numpy()) < RTOL and rel_err(bs.grad, br.grad.numpy()) < RTOL
+    small = hgr.ops.linear(torch.ones(8, k, device="cuda"), ws.detach(), bs.detach(), relu=relu)  # short inputs stay on F.linear
+    assert small.shape == (8, w)
+
+
 def test_scatter_mean_form_matches_reference_golden_and_oracle(hgr, golden):
     from hypergraph_diffusion_for_recommendation_b200 import graph
 
