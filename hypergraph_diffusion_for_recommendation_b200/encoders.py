@@ -15,6 +15,8 @@ keeps working when these are imported instead:
 ``EquivSetGNN``               model/graph/HGNN_HD3.py:555-610
 ``LocalAwareEncoder``         model/graph/HGNN_HD3.py:352-427
 ``HCCFEncoder``               model/graph/HCCF.py:136-191 (+ GCNLayer :193-199, HGNNLayer :201-211)
+``SHTEncoder``                model/graph/SHT.py:142-203
+``DHCF_Encoder``              model/graph/DHCF.py:135-186
 ===========================  ==================================================================
 
 What changes underneath: every ``torch.sparse.mm`` is ``ops.spmm`` / ``ops.hgconv`` /
@@ -476,6 +478,109 @@ class HCCFEncoder(nn.Module):
             hidden += [gcn_emb + hgnn_hidden[-1]]
         embeddings = sum(hidden)
         return embeddings[:n_users], embeddings[n_users:], gcn_hidden, hgnn_hidden
+
+
+class SHTEncoder(nn.Module):
+    """``SHTEncoder`` (model/graph/SHT.py:142-203): LightGCN propagation with SUM readout over the normalised adjacency, then the
+    low-rank hypergraph transform ``embeds @ (hyper.T @ hyper)`` on the detached user and item halves.  Same constructor, parameter
+    names (``uEmbeds``, ``iEmbeds``, ``uHyper``, ``iHyper``) and return triple as the reference."""
+
+    def __init__(self, data, args):
+        super(SHTEncoder, self).__init__()
+        init = nn.init.xavier_uniform_
+        self.args = args
+        self.data = data
+        self.n_user = self.data.n_users
+        self.n_item = self.data.n_items
+        self._parse_config(args)
+        self.norm_adj = self.data.norm_adj
+        self.sparse_norm_adj = _adjacency_of(data)
+        self.uEmbeds = nn.Parameter(init(torch.empty(self.n_user, self.embeddingSize)))
+        self.iEmbeds = nn.Parameter(init(torch.empty(self.n_item, self.embeddingSize)))
+        self.uHyper = nn.Parameter(init(torch.empty(args['hyperedge_num'], self.embeddingSize)))
+        self.iHyper = nn.Parameter(init(torch.empty(args['hyperedge_num'], self.embeddingSize)))
+
+    def _parse_config(self, kwargs):
+        self.maxEpoch = int(kwargs['max_epoch'])
+        self.batchSize = int(kwargs['batch_size'])
+        self.lRate = float(kwargs['lrate'])
+        self.lr_decay = float(kwargs['lr_decay'])
+        self.reg = float(kwargs['reg'])
+        self.latent_size = int(kwargs['embedding_size'])
+        self.embeddingSize = int(kwargs['hyper_dim'])
+        self.hyperDim = int(kwargs['hyper_dim'])
+        self.dropRate = float(kwargs['drop_rate'])
+        self.negSlove = float(kwargs['p'])
+        self.nLayers = int(kwargs['n_layers'])
+        self.ss_rate = float(kwargs['cl_rate'])
+        self.temp = float(kwargs['temp'])
+        self.seed = int(kwargs['seed'])
+        self.edgeSampRate = 0.1
+        self.ssl1_reg = 0.1
+        self.ssl2_reg = 0.1
+        self.early_stopping_steps = int(kwargs['early_stopping_steps'])
+        self.hyperedge_num = int(kwargs['hyperedge_num'])
+
+    def gcnLayer(self, adj, embeds):
+        return ops.spmm(adj, embeds)
+
+    def hgnnLayer(self, embeds, hyper):
+        small = hyper.T @ hyper  # [D, D]
+        if ops.tall_times_small_supported(embeds, small):
+            return ops.tall_times_small(embeds, small)
+        return embeds @ small
+
+    def forward(self):
+        embeds = torch.concat([self.uEmbeds, self.iEmbeds], dim=0)
+        # lats = [E, A E, A^2 E, ...]; embeds = sum(lats): the fused propagation with the sum readout (SHT.py:192-199)
+        embeds = ops.lightgcn_propagate(self.sparse_norm_adj, embeds, self.nLayers, sum_readout=True)
+        # this detach helps eliminate the mutual influence between the local GCN and the global HGNN (SHT.py:200)
+        hyperUEmbeds = self.hgnnLayer(embeds[:self.n_user].detach(), self.uHyper)
+        hyperIEmbeds = self.hgnnLayer(embeds[self.n_user:].detach(), self.iHyper)
+        return embeds, hyperUEmbeds, hyperIEmbeds
+
+
+class DHCF_Encoder(nn.Module):
+    """``DHCF_Encoder`` (model/graph/DHCF.py:135-186): ``HGCNConv`` on the RECTANGULAR user x item interaction matrix --
+    ``leaky(R (R^T U))`` for users, ``leaky(R^T (R I))`` for items, every layer applied to the INPUT tables as in the reference --
+    and a concatenation readout.  The reference densifies ``R`` (``.to_dense()``, U x I floats); here it stays a ``DeviceCSR``."""
+
+    def __init__(self, config, data, args):
+        super(DHCF_Encoder, self).__init__()
+        self.data = data
+        self.adj = TorchGraphInterface.convert_sparse_mat_to_tensor(data.interaction_mat)
+        self._parse_args(args)
+        self.embedding_dict = self._init_model()
+        self.fc_u = nn.Linear(self.hyper_dim, self.hyper_dim)
+        self.fc_i = nn.Linear(self.hyper_dim, self.hyper_dim)
+        self.hgnn_u = [HGCNConv(leaky=self.p) for _ in range(self.layers)]
+        self.hgnn_i = [HGCNConv(leaky=self.p) for _ in range(self.layers)]
+        self.non_linear = nn.ReLU()
+        self.dropout = nn.Dropout(self.drop_rate)
+
+    def _parse_args(self, args):
+        self.input_dim = args['input_dim']
+        self.hyper_dim = args['hyper_dim']
+        self.p = args['p']
+        self.drop_rate = args['drop_rate']
+        self.layers = args['n_layers']
+
+    def _init_model(self):
+        initializer = nn.init.xavier_uniform_
+        return nn.ParameterDict({
+            'user_emb': nn.Parameter(initializer(torch.empty(self.data.n_users, self.hyper_dim))),
+            'item_emb': nn.Parameter(initializer(torch.empty(self.data.n_items, self.hyper_dim))),
+        })
+
+    def forward(self):
+        uEmbed = self.embedding_dict['user_emb']
+        iEmbed = self.embedding_dict['item_emb']
+        user_embeds = [uEmbed]
+        item_embeds = [iEmbed]
+        for idx in range(self.layers):
+            user_embeds.append(self.hgnn_u[idx](self.adj, uEmbed))
+            item_embeds.append(self.hgnn_i[idx](self.adj.t(), iEmbed))
+        return torch.cat(user_embeds, dim=1), torch.cat(item_embeds, dim=1)
 
 
 class HGNNModel(nn.Module):

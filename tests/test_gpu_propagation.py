@@ -408,3 +408,50 @@ def test_sgl_encoder_views_and_device_augmentor(hgr, pl_graph):
     # per-layer list of perturbed graphs (aug_type 2 in the paper) gives the same result as one graph used for every layer
     a, b = enc([p1, p1, p1]), enc(p1)
     assert rel_err(a[0], b[0]) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ more callers of the path
+@pytest.fixture(scope="module")
+def more_golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "more_encoders.npz"))
+
+
+def _facade(more_golden):
+    from hypergraph_diffusion_for_recommendation_b200 import data as D
+
+    return D.Interaction(None, more_golden["train"].tolist(), more_golden["test"].tolist())
+
+
+def test_sht_encoder_matches_reference(hgr, more_golden):
+    """SHTEncoder (LightGCN-sum + low-rank hypergraph transform) on the façade's device adjacency against the reference's
+    CPU outputs and parameter gradients (tests/golden/make_golden_more_encoders.py)."""
+    g = more_golden
+    n_layers, hyper_dim, n_hyper = (int(v) for v in g["sht_args"])
+    args = {"max_epoch": 1, "batch_size": 64, "lrate": 0.01, "lr_decay": 0.9, "reg": 0.0, "embedding_size": 64, "hyper_dim": hyper_dim,
+            "drop_rate": 0.2, "p": 0.1, "n_layers": n_layers, "cl_rate": 1e-4, "temp": 0.2, "seed": 20, "early_stopping_steps": 20,
+            "hyperedge_num": n_hyper}
+    m = hgr.enc.SHTEncoder(_facade(g), args).cuda()
+    m.load_state_dict(params(g, "sht_param/"), strict=True)
+    emb, hu, hi = m()
+    assert rel_err(emb, g["sht_embeds"]) < RTOL and rel_err(hu, g["sht_hyper_u"]) < RTOL and rel_err(hi, g["sht_hyper_i"]) < RTOL
+    ((emb * cuda(g["sht_w0"])).sum() + (hu * cuda(g["sht_w1"])).sum() + (hi * cuda(g["sht_w2"])).sum()).backward()
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, g["sht_grad/" + k]) < 2e-5, k
+
+
+def test_dhcf_encoder_rectangular_hgconv_matches_reference(hgr, more_golden):
+    """DHCF_Encoder: HGCNConv on the rectangular [users, items] interaction matrix and on its transpose (the reference densifies
+    the matrix); outputs and embedding gradients against the reference."""
+    g = more_golden
+    layers, hyper_dim, p = int(g["dhcf_args"][0]), int(g["dhcf_args"][1]), float(g["dhcf_args"][2])
+    m = hgr.enc.DHCF_Encoder(None, _facade(g), {"input_dim": 64, "hyper_dim": hyper_dim, "p": p, "drop_rate": 0.2, "n_layers": layers}).cuda()
+    m.load_state_dict(params(g, "dhcf_param/"), strict=True)
+    assert m.adj.shape == (m.data.n_users, m.data.n_items) and m.adj.t().shape == (m.data.n_items, m.data.n_users)
+    ue, ie = m()
+    assert ue.shape[1] == (layers + 1) * hyper_dim
+    assert rel_err(ue, g["dhcf_user_out"]) < RTOL and rel_err(ie, g["dhcf_item_out"]) < RTOL
+    ((ue * cuda(g["dhcf_wu"])).sum() + (ie * cuda(g["dhcf_wi"])).sum()).backward()
+    assert rel_err(m.embedding_dict["user_emb"].grad, g["dhcf_grad_user"]) < 2e-5
+    assert rel_err(m.embedding_dict["item_emb"].grad, g["dhcf_grad_item"]) < 2e-5
