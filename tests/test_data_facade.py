@@ -232,3 +232,14 @@ def test_eval_and_sampler_take_the_facade_without_python_loops(gold):
         assert u.dtype == torch.int64 and u.numel() == p.numel() == n.numel()
         for uu, pp, nn in zip(u.tolist(), p.tolist(), n.tolist()):
             assert (uu, pp) in tr and (uu, nn) not in tr
+
+
+def test_empty_and_single_interaction_lists():
+    d = D.Interaction(None, [], [])
+    assert (d.n_users, d.n_items) == (0, 0) and d.training_size() == (0, 0, 0) and d.test_size() == (0, 0, 0)
+    assert list(d.test_set) == [] and d.user_rated(5) == ([], []) and d.contain(1, 2) is False and d.get_user_id(1) is None
+    d = D.Interaction(None, [[1, 2, 1.0]], [[1, 3, 1.0], [9, 9, 1.0]])  # the test entry of the unknown user 9 is skipped
+    assert d.training_size() == (1, 1, 1) and d.test_size() == (1, 1, 2)
+    assert dict(d.test_set[1]) == {3: 1.0} and d.user_rated(1) == ([2], [1.0]) and d.test_set_item == {3}
+    users, raw, ptr, truth, id2item = d.eval_arrays()
+    assert users.tolist() == [0] and raw == [1] and ptr.tolist() == [0, 1] and truth.tolist() == [-1] and id2item.tolist() == [2]
