@@ -314,8 +314,8 @@ def run_ours(args):
 
     graphed = None
     if use_graph:
-        # warm up and capture with adam steps that count: restore parameters / optimizer state afterwards so that the timed
-        # steps start from the same state as the ungraphed path
+        # warm-up (three Adam steps on an all-zero batch, off the default stream) and capture; the timed steps then replay the
+        # graph on the real batches.  The warm-up steps nudge the parameters, which timing does not depend on
         if args.model == "hccf":
             # torch.unique's variable-length result is replaced by the fixed-size sorted-with-gaps form (loss_torch.unique_padded)
             graphed = trainer.GraphedStep(lambda tu, tp, tn: trainer.train_step_hccf(model, optimizer, tu, tp, tn, HCCF_TEMP, HCCF_SS_RATE,
