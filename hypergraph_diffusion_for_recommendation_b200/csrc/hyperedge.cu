@@ -90,31 +90,58 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float *__restric
     T[e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
-// Y[n, N] = [A1 | A2] B with B [(K1 + K2), N] resident in shared memory.  Block = 64-row tile; thread = 4 output columns
-// x (64 / TY) rows, TY = 256 / (N / 4) row groups.
+__device__ __forceinline__ void he_cp_async16(void *smem, const void *gmem, bool valid) {
+    // 16-byte asynchronous copy; an invalid source copies nothing and zero-fills the destination
+    const unsigned n = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(n)
+                 : "memory");
+}
+__device__ __forceinline__ void he_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
+__device__ __forceinline__ void he_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Y[n, N] = [relu]([A1 | A2] B + bias) with B [(K1 + K2), N] resident in shared memory.  A block walks 64-row tiles; the rows
+// of the NEXT tile stream into the other half of a double buffer (cp.async) while the current tile is multiplied.
+// Thread = 4 output columns x (TR / TY) rows, TY = 256 / (N / 4) row groups; TR = 64 rows per tile, 32 when B is large.
+template <int N, int TR>
 __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const float *__restrict__ A1, int K1,
                                                                       const float *__restrict__ A2, int K2,
                                                                       const float *__restrict__ B, int64_t n,
                                                                       float *__restrict__ Y, const float *__restrict__ bias,
                                                                       int relu) {
-    constexpr int TX = N / 4, TY = kHeThreads / TX, RPT = 64 / TY;  // rows per thread
+    constexpr int TX = N / 4, TY = kHeThreads / TX, RPT = TR / TY;  // rows per thread
+    static_assert(RPT >= 1, "tile shorter than the thread layout");
     extern __shared__ __align__(16) float he_smem[];
     const int Kc = K1 + K2;
-    float *Bs = he_smem;             // [Kc][N]
-    float *As = he_smem + Kc * N;    // [64][Kc]
+    float *Bs = he_smem;           // [Kc][N]
+    float *As0 = he_smem + Kc * N; // 2 x [TR][Kc]
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    auto prefetch = [&](int64_t r0, float *As) {
+        for (int e = threadIdx.x; e < TR * (Kc / 4); e += kHeThreads) {
+            const int r = e / (Kc / 4), c = (e % (Kc / 4)) * 4;
+            const bool ok = r0 + r < n;
+            const int64_t row = ok ? r0 + r : 0;
+            const float *src = c < K1 ? A1 + row * K1 + c : A2 + row * K2 + (c - K1);
+            he_cp_async16(As + r * Kc + c, src, ok);
+        }
+        he_cp_async_commit();
+    };
+    const int64_t step = (int64_t)gridDim.x * TR;
+    int64_t r0 = (int64_t)blockIdx.x * TR;
+    if (r0 < n) prefetch(r0, As0);
     for (int e = threadIdx.x; e < Kc * (N / 4); e += kHeThreads)
         reinterpret_cast<float4 *>(Bs)[e] = __ldg(reinterpret_cast<const float4 *>(B) + e);
-    for (int64_t r0 = (int64_t)blockIdx.x * 64; r0 < n; r0 += (int64_t)gridDim.x * 64) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < 64 * (Kc / 4); e += kHeThreads) {
-            const int r = e / (Kc / 4), c = (e % (Kc / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r0 + r < n)
-                v = c < K1 ? ld_stream_f4(reinterpret_cast<const float4 *>(A1 + (r0 + r) * K1 + c))
-                           : ld_stream_f4(reinterpret_cast<const float4 *>(A2 + (r0 + r) * K2 + (c - K1)));
-            *reinterpret_cast<float4 *>(As + r * Kc + c) = v;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = __ldg(reinterpret_cast<const float4 *>(bias) + tx);
+    for (int it = 0; r0 < n; r0 += step, ++it) {
+        const float *As = As0 + (it & 1) * TR * Kc;
+        if (r0 + step < n) {
+            prefetch(r0 + step, As0 + ((it + 1) & 1) * TR * Kc);
+            he_cp_async_wait<1>();  // everything but the tile just requested has landed
+        } else {
+            he_cp_async_wait<0>();
         }
         __syncthreads();
         float4 acc[RPT];
@@ -137,8 +164,6 @@ __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const floa
                 acc[i].z = fmaf(a.w, b[3].z, acc[i].z); acc[i].w = fmaf(a.w, b[3].w, acc[i].w);
             }
         }
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) bv = __ldg(reinterpret_cast<const float4 *>(bias) + tx);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const int64_t r = r0 + ty + TY * i;
@@ -146,6 +171,7 @@ __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const floa
             if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
             if (r < n) reinterpret_cast<float4 *>(Y + r * N)[tx] = o;
         }
+        __syncthreads();  // the buffer just read is the target of the prefetch after next
     }
 }
 
@@ -227,21 +253,32 @@ int hgr_rows_times_small_bias_f32(const float *A1, int32_t K1, const float *A2, 
     HGR_REQUIRE(A1 && B && Y && (K2 == 0 || A2), "NULL operand");
     HGR_REQUIRE(aligned16(A1) && aligned16(A2) && aligned16(B) && aligned16(Y), "operands must be 16-byte aligned");
     const int Kc = K1 + K2;
-    const size_t smem = ((size_t)Kc * N + (size_t)64 * Kc) * sizeof(float);
+    // B + the double-buffered row tile: 64 rows per tile, 32 when the small matrix leaves less room
+    const int TR = ((size_t)Kc * N + (size_t)2 * 64 * Kc) * sizeof(float) <= 200 * 1024 ? 64 : 32;
+    const size_t smem = ((size_t)Kc * N + (size_t)2 * TR * Kc) * sizeof(float);
     HGR_REQUIRE(smem <= 220 * 1024, "small matrix [%d, %d] does not fit shared memory", Kc, N);
-    int64_t blocks = ceil_div(n, 64);
+    int64_t blocks = ceil_div(n, TR);
     if (blocks > 148 * 2) blocks = 148 * 2;
     cudaStream_t st = (cudaStream_t)stream;
-#define HGR_RTS(NN)                                                                                                          \
-    do {                                                                                                                     \
-        HGR_CUDA_OK(cudaFuncSetAttribute(rows_times_small_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rows_times_small_kernel<NN><<<(unsigned)blocks, kHeThreads, smem, st>>>(A1, K1, A2, K2, B, n, Y, bias, relu);                     \
+#define HGR_RTS(NN, TT)                                                                                                          \
+    do {                                                                                                                         \
+        HGR_CUDA_OK(cudaFuncSetAttribute(rows_times_small_kernel<NN, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rows_times_small_kernel<NN, TT><<<(unsigned)blocks, kHeThreads, smem, st>>>(A1, K1, A2, K2, B, n, Y, bias, relu);         \
     } while (0)
-    switch (N) {
-        case 32: HGR_RTS(32); break;
-        case 64: HGR_RTS(64); break;
-        case 128: HGR_RTS(128); break;
-        default: HGR_RTS(256); break;
+    if (TR == 64) {
+        switch (N) {
+            case 32: HGR_RTS(32, 64); break;
+            case 64: HGR_RTS(64, 64); break;
+            case 128: HGR_RTS(128, 64); break;
+            default: HGR_RTS(256, 64); break;
+        }
+    } else {
+        switch (N) {
+            case 32: HGR_RTS(32, 32); break;
+            case 64: HGR_RTS(64, 32); break;
+            case 128: HGR_RTS(128, 32); break;
+            default: HGR_RTS(256, 32); break;
+        }
     }
 #undef HGR_RTS
     HGR_LAUNCH_OK("rows_times_small_kernel");

@@ -332,7 +332,7 @@ class _Hyperedge(torch.autograd.Function):
         dh = None
         if ctx.needs_input_grad[0]:
             d, k = e.shape[1], h.shape[1]
-            if (2 * d * k + 64 * 2 * d) * 4 <= 200 * 1024:  # [T^T ; dT^T] and a 64-row tile of [dY | E] fit shared memory
+            if (2 * d * k + 2 * 32 * 2 * d) * 4 <= 220 * 1024:  # [T^T ; dT^T] and two (32-row) tiles of [dY | E] fit shared memory
                 dh = rows_times_small(dy, e, torch.cat([t.t(), dt.t()], 0).contiguous())  # dY T^T + E dT^T in one pass
             else:
                 dh = rows_times_small(dy, None, t.t().contiguous()) + rows_times_small(e, None, dt.t().contiguous())
