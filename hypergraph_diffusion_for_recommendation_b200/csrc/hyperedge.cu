@@ -19,14 +19,26 @@ namespace hgr {
 constexpr int kHeThreads = 256;
 constexpr int kHeRows = 32;  // rows staged per step of the reduce kernel
 
+__device__ __forceinline__ void he_cp_async16(void *smem, const void *gmem, bool valid) {
+    // 16-byte asynchronous copy; an invalid source copies nothing and zero-fills the destination
+    const unsigned n = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(n)
+                 : "memory");
+}
+__device__ __forceinline__ void he_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void he_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // T_partial[block][K][D] = sum over the block's rows of H[r, :]^T E[r, :].
 // Thread (tk, td) of a 16 x 16 layout owns the KT x DT block T[tk * KT ..][td * DT ..]; K = 16 KT, D = 16 DT.
 template <int KT, int DT>
 __global__ void __launch_bounds__(kHeThreads) tall_skinny_tn_kernel(const float *__restrict__ H, const float *__restrict__ E,
                                                                     int64_t n, int ldh, float *__restrict__ partials) {
     constexpr int K = 16 * KT, D = 16 * DT;
-    __shared__ __align__(16) float Hs[kHeRows][K];
-    __shared__ __align__(16) float Es[kHeRows][D];
+    extern __shared__ __align__(16) float ts_smem[];  // 2 x ([kHeRows][K] rows of H | [kHeRows][D] rows of E)
+    constexpr int kTile = kHeRows * (K + D);
     const int td = threadIdx.x % 16, tk = threadIdx.x / 16;
     float acc[KT][DT];
 #pragma unroll
@@ -37,34 +49,45 @@ __global__ void __launch_bounds__(kHeThreads) tall_skinny_tn_kernel(const float 
     const int64_t per = (n + gridDim.x - 1) / gridDim.x;
     const int64_t r_begin = (int64_t)blockIdx.x * per;
     const int64_t r_end = r_begin + per < n ? r_begin + per : n;
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += kHeRows) {
-        const int rows = (int)(r_end - r0 < kHeRows ? r_end - r0 : kHeRows);
-        __syncthreads();
+    // the next 32-row tile streams in (cp.async, rows past the slice zero-filled) while the current one is accumulated
+    auto prefetch = [&](int64_t r0, float *buf) {
+        float *Hs = buf, *Es = buf + kHeRows * K;
         for (int e = threadIdx.x; e < kHeRows * (K / 4); e += kHeThreads) {
             const int r = e / (K / 4), c = e % (K / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < rows) v = ld_stream_f4(reinterpret_cast<const float4 *>(H + (r0 + r) * ldh) + c);
-            reinterpret_cast<float4 *>(&Hs[r][0])[c] = v;
+            const bool ok = r0 + r < r_end;
+            he_cp_async16(Hs + r * K + 4 * c, H + (ok ? r0 + r : 0) * ldh + 4 * c, ok);
         }
         for (int e = threadIdx.x; e < kHeRows * (D / 4); e += kHeThreads) {
             const int r = e / (D / 4), c = e % (D / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < rows) v = ld_stream_f4(reinterpret_cast<const float4 *>(E + (r0 + r) * D) + c);
-            reinterpret_cast<float4 *>(&Es[r][0])[c] = v;
+            const bool ok = r0 + r < r_end;
+            he_cp_async16(Es + r * D + 4 * c, E + (ok ? r0 + r : 0) * D + 4 * c, ok);
+        }
+        he_cp_async_commit();
+    };
+    if (r_begin < r_end) prefetch(r_begin, ts_smem);
+    int it = 0;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kHeRows, ++it) {
+        const float *Hs = ts_smem + (it & 1) * kTile, *Es = Hs + kHeRows * K;
+        if (r0 + kHeRows < r_end) {
+            prefetch(r0 + kHeRows, ts_smem + ((it + 1) & 1) * kTile);
+            he_cp_async_wait<1>();
+        } else {
+            he_cp_async_wait<0>();
         }
         __syncthreads();
 #pragma unroll 4
-        for (int r = 0; r < kHeRows; ++r) {  // zero-padded rows add nothing
+        for (int r = 0; r < kHeRows; ++r) {  // zero-filled rows add nothing
             float h[KT], x[DT];
 #pragma unroll
-            for (int a = 0; a < KT; ++a) h[a] = Hs[r][tk * KT + a];
+            for (int a = 0; a < KT; ++a) h[a] = Hs[r * K + tk * KT + a];
 #pragma unroll
-            for (int b = 0; b < DT; ++b) x[b] = Es[r][td * DT + b];
+            for (int b = 0; b < DT; ++b) x[b] = Es[r * D + td * DT + b];
 #pragma unroll
             for (int a = 0; a < KT; ++a)
 #pragma unroll
                 for (int b = 0; b < DT; ++b) acc[a][b] = fmaf(h[a], x[b], acc[a][b]);
         }
+        __syncthreads();  // the buffer just read is the target of the prefetch after next
     }
     float *out = partials + (size_t)blockIdx.x * K * D;
 #pragma unroll
@@ -88,18 +111,6 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float *__restric
     }
     for (int c = 0; b < n_blocks; ++b, ++c) s[c] += partials[(size_t)b * n_elems + e];
     T[e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-}
-
-__device__ __forceinline__ void he_cp_async16(void *smem, const void *gmem, bool valid) {
-    // 16-byte asynchronous copy; an invalid source copies nothing and zero-fills the destination
-    const unsigned n = valid ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(n)
-                 : "memory");
-}
-__device__ __forceinline__ void he_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void he_cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // Y[n, N] = [relu]([A1 | A2] B + bias) with B [(K1 + K2), N] resident in shared memory.  A block walks 64-row tiles; the rows
@@ -184,12 +195,19 @@ static int reduce_blocks(int64_t n) {
 
 static bool small_dim_ok(int v) { return v == 32 || v == 64 || v == 128; }
 
+template <int KT, int DT>
+static void launch_tn_one(int blocks, cudaStream_t st, const float *H, const float *E, int64_t n, int ldh, float *partials) {
+    const size_t smem = (size_t)2 * kHeRows * (16 * KT + 16 * DT) * sizeof(float);  // <= 64 KB
+    cudaFuncSetAttribute(tall_skinny_tn_kernel<KT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tall_skinny_tn_kernel<KT, DT><<<blocks, kHeThreads, smem, st>>>(H, E, n, ldh, partials);
+}
+
 template <int KT>
 static void launch_tn(int D, int blocks, cudaStream_t st, const float *H, const float *E, int64_t n, int ldh, float *partials) {
     switch (D) {
-        case 32: tall_skinny_tn_kernel<KT, 2><<<blocks, kHeThreads, 0, st>>>(H, E, n, ldh, partials); break;
-        case 64: tall_skinny_tn_kernel<KT, 4><<<blocks, kHeThreads, 0, st>>>(H, E, n, ldh, partials); break;
-        default: tall_skinny_tn_kernel<KT, 8><<<blocks, kHeThreads, 0, st>>>(H, E, n, ldh, partials); break;
+        case 32: launch_tn_one<KT, 2>(blocks, st, H, E, n, ldh, partials); break;
+        case 64: launch_tn_one<KT, 4>(blocks, st, H, E, n, ldh, partials); break;
+        default: launch_tn_one<KT, 8>(blocks, st, H, E, n, ldh, partials); break;
     }
 }
 
