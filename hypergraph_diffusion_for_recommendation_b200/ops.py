@@ -163,11 +163,14 @@ def spmm(adj: DeviceCSR, x: torch.Tensor) -> torch.Tensor:
 
 class _HGConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, a, slope, eps):
+    def forward(ctx, x, gamma, beta, residual, a, slope, eps, residual_is_x=False):
         need_pre = (slope is not None or gamma is not None) and any(ctx.needs_input_grad[:3])
         pre = torch.empty((a.shape[0], x.shape[1]), dtype=torch.float32, device=x.device) if need_pre else None
         g = gamma.contiguous() if gamma is not None else None
         b = beta.contiguous() if beta is not None else None
+        if residual_is_x:  # y = f(x) + x (EquivSetConv's two convolutions): the residual gradient rides on the backward epilogue
+            residual = x
+        ctx.res_is_x = residual_is_x
         r = _check_dense(residual, a.shape[0], "residual") if residual is not None else None
         y = hgconv_raw(a, a.t(), x, _epilogue(slope=slope, gamma=g, beta=b, eps=eps, residual=r, pre=pre))
         ctx.a, ctx.slope, ctx.eps = a, slope, eps
@@ -185,8 +188,16 @@ class _HGConv(torch.autograd.Function):
         else:
             dz = dy
         # y = f(A (At x))  =>  dx = At^T (A^T dz) = A (At dz) evaluated with the roles swapped
+        if ctx.res_is_x:
+            # dx = A (At dz) + dy in the second propagation's epilogue instead of a separate elementwise add
+            dx = hgconv_raw(ctx.a, ctx.a.t(), dz, _epilogue(residual=dy)) if ctx.needs_input_grad[0] else None
+            return dx, dgamma, dbeta, None, None, None, None, None
         dx = _hgconv_transposed(ctx.a, dz) if ctx.needs_input_grad[0] else None
-        return dx, dgamma, dbeta, (dy if ctx.has_res else None), None, None, None
+        return dx, dgamma, dbeta, (dy if ctx.has_res else None), None, None, None, None
+
+
+def a_is_square(a) -> bool:
+    return a.shape[0] == a.shape[1]
 
 
 def _hgconv_transposed(a: DeviceCSR, dz: torch.Tensor) -> torch.Tensor:
@@ -205,6 +216,8 @@ def hgconv(adj: DeviceCSR, x: torch.Tensor, slope: float | None = None, ln_weigh
         raise ValueError("ln_weight and ln_bias must be given together")
     if _sharded(adj):
         return adj.hgconv(x, slope, ln_weight, ln_bias, residual, eps)
+    if residual is x and residual is not None and a_is_square(adj):
+        return _HGConv.apply(x, ln_weight, ln_bias, None, adj, slope, eps, True)
     return _HGConv.apply(x, ln_weight, ln_bias, residual, adj, slope, eps)
 
 
