@@ -196,18 +196,19 @@ static int reduce_blocks(int64_t n) {
 static bool small_dim_ok(int v) { return v == 32 || v == 64 || v == 128; }
 
 template <int KT, int DT>
-static void launch_tn_one(int blocks, cudaStream_t st, const float *H, const float *E, int64_t n, int ldh, float *partials) {
+static int launch_tn_one(int blocks, cudaStream_t st, const float *H, const float *E, int64_t n, int ldh, float *partials) {
     const size_t smem = (size_t)2 * kHeRows * (16 * KT + 16 * DT) * sizeof(float);  // <= 64 KB
-    cudaFuncSetAttribute(tall_skinny_tn_kernel<KT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HGR_CUDA_OK(cudaFuncSetAttribute(tall_skinny_tn_kernel<KT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tall_skinny_tn_kernel<KT, DT><<<blocks, kHeThreads, smem, st>>>(H, E, n, ldh, partials);
+    return HGR_OK;
 }
 
 template <int KT>
-static void launch_tn(int D, int blocks, cudaStream_t st, const float *H, const float *E, int64_t n, int ldh, float *partials) {
+static int launch_tn(int D, int blocks, cudaStream_t st, const float *H, const float *E, int64_t n, int ldh, float *partials) {
     switch (D) {
-        case 32: launch_tn_one<KT, 2>(blocks, st, H, E, n, ldh, partials); break;
-        case 64: launch_tn_one<KT, 4>(blocks, st, H, E, n, ldh, partials); break;
-        default: launch_tn_one<KT, 8>(blocks, st, H, E, n, ldh, partials); break;
+        case 32: return launch_tn_one<KT, 2>(blocks, st, H, E, n, ldh, partials);
+        case 64: return launch_tn_one<KT, 4>(blocks, st, H, E, n, ldh, partials);
+        default: return launch_tn_one<KT, 8>(blocks, st, H, E, n, ldh, partials);
     }
 }
 
@@ -243,11 +244,13 @@ int hgr_tall_skinny_tn_f32(const float *H, const float *E, int64_t n, int32_t K,
     const int halves = K == 256 ? 2 : 1, Kh = K / halves;
     for (int h = 0; h < halves; ++h) {
         float *part = partials + (size_t)h * blocks * Kh * D;
+        int rc;
         switch (Kh) {
-            case 32: launch_tn<2>(D, blocks, st, H + h * Kh, E, n, K, part); break;
-            case 64: launch_tn<4>(D, blocks, st, H + h * Kh, E, n, K, part); break;
-            default: launch_tn<8>(D, blocks, st, H + h * Kh, E, n, K, part); break;
+            case 32: rc = launch_tn<2>(D, blocks, st, H + h * Kh, E, n, K, part); break;
+            case 64: rc = launch_tn<4>(D, blocks, st, H + h * Kh, E, n, K, part); break;
+            default: rc = launch_tn<8>(D, blocks, st, H + h * Kh, E, n, K, part); break;
         }
+        if (rc) return rc;
         HGR_LAUNCH_OK("tall_skinny_tn_kernel");
         partial_sum_kernel<<<(Kh * D + 255) / 256, 256, 0, st>>>(part, blocks, Kh * D, T + (size_t)h * Kh * D);
         HGR_LAUNCH_OK("partial_sum_kernel");
