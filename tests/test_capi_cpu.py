@@ -109,3 +109,31 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhgr.so")
     with pytest.raises(_lib.HgrError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_unique_padded_is_torch_unique_with_gaps():
+    """Host logic of the capturable HCCF step: sorted ids, repeats replaced by -1, active entries in torch.unique's order."""
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200 import loss_torch
+
+    g = torch.Generator().manual_seed(3)
+    for n, hi in ((1, 5), (64, 10), (4096, 3000)):
+        idx = torch.randint(0, hi, (n,), generator=g)
+        pad = loss_torch.unique_padded(idx)
+        assert pad.shape == idx.shape and pad.dtype == idx.dtype
+        assert torch.equal(pad[pad >= 0], torch.unique(idx))
+        assert int((pad < 0).sum()) == n - int(torch.unique(idx).numel())
+
+
+def test_shape_predicates_refuse_cpu_tensors_and_odd_widths():
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200 import ops
+
+    assert not ops.hyperedge_supported(torch.ones(8, 128), torch.ones(8, 64))  # CPU tensors: no kernel path
+    assert not ops.tall_times_small_supported(torch.ones(8, 64), torch.ones(64, 128))
+    import pytest
+
+    with pytest.raises(ValueError):
+        ops.hyperedge(torch.ones(8, 128), torch.ones(8, 64))
