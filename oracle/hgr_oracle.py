@@ -181,6 +181,37 @@ def lgcn_forward(csr, user_emb, item_emb, n_layers):
     return mean[: user_emb.shape[0]], mean[user_emb.shape[0]:]
 
 
+def sht_forward(csr, u_emb, i_emb, u_hyper, i_hyper, n_layers):
+    """``SHTEncoder.forward`` (model/graph/SHT.py:192-203): ``embeds = sum_k A^k E`` (k = 0..L), then the low-rank hypergraph
+    transform ``embeds @ (hyper.T @ hyper)`` on the user and item halves (float64 accumulation, rounded once)."""
+    ego = np.concatenate([u_emb, i_emb], 0).astype(np.float32)
+    lats = [ego]
+    for _ in range(n_layers):
+        lats.append(spmm(*csr, lats[-1]))
+    emb = lats[0].copy()
+    for t in lats[1:]:
+        emb = emb + t
+    n_u = u_emb.shape[0]
+
+    def hg(e, h):
+        h64 = h.astype(np.float64)
+        return (e.astype(np.float64) @ (h64.T @ h64)).astype(np.float32)
+
+    return emb, hg(emb[:n_u], u_hyper), hg(emb[n_u:], i_hyper)
+
+
+def dhcf_forward(r_csr, u_emb, i_emb, n_layers, slope):
+    """``DHCF_Encoder.forward`` (model/graph/DHCF.py:170-186): per layer ``leaky(R (R^T U))`` and ``leaky(R^T (R I))`` of the INPUT
+    tables (the reference does not chain the layers), concatenated after the inputs along the feature axis.  ``r_csr`` is the
+    ``[users, items]`` interaction matrix (the reference densifies it; the products are the same sums)."""
+    rt = csr_transpose(*r_csr, i_emb.shape[0])
+    us, its = [u_emb], [i_emb]
+    for _ in range(n_layers):
+        us.append(hgconv(r_csr, u_emb, slope, csr_t=rt))
+        its.append(hgconv(rt, i_emb, slope, csr_t=r_csr))
+    return np.concatenate(us, 1), np.concatenate(its, 1)
+
+
 def leaky_relu(x, slope):
     return np.where(x >= 0, x, x * np.float32(slope)).astype(np.float32)
 

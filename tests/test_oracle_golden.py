@@ -225,3 +225,28 @@ def test_torch_path_losses_and_eval_match_reference(golden, pl_graph):
     tip, tix, _ = O.interaction_matrix(pl_graph["u"], pl_graph["i"], pl_graph["n_users"], pl_graph["n_items"])
     rec = T.evaluate_users(torch.from_numpy(golden["eval_user_emb"]), torch.from_numpy(golden["eval_item_emb"]), test_users, tip, tix, 20)
     assert np.array_equal(golden["pl_id2item"][rec], golden["eval_rec_items_raw"])
+
+
+def test_sht_and_dhcf_encoders_against_the_reference():
+    """The oracle's restatements of two more callers of the path (SHTEncoder, DHCF_Encoder) against the reference's own outputs
+    (tests/golden/more_encoders.npz, make_golden_more_encoders.py)."""
+    import os
+
+    from hypergraph_diffusion_for_recommendation_b200 import data as D
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "more_encoders.npz"))
+    d = D.Interaction(None, g["train"].tolist(), g["test"].tolist())
+    u, i = d.dense_training_pairs()
+    csr = O.build_norm_adj(u, i, d.n_users, d.n_items)
+    n_layers = int(g["sht_args"][0])
+    emb, hu, hi = O.sht_forward(csr, g["sht_param/uEmbeds"], g["sht_param/iEmbeds"], g["sht_param/uHyper"], g["sht_param/iHyper"], n_layers)
+
+    def rel(a, b):
+        return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / np.abs(b).max()
+
+    assert rel(emb, g["sht_embeds"]) < 1e-6 and rel(hu, g["sht_hyper_u"]) < 1e-5 and rel(hi, g["sht_hyper_i"]) < 1e-5
+    r = O.interaction_matrix(u, i, d.n_users, d.n_items)
+    ue, ie = O.dhcf_forward(r, g["dhcf_param/embedding_dict.user_emb"], g["dhcf_param/embedding_dict.item_emb"], int(g["dhcf_args"][0]),
+                            float(g["dhcf_args"][2]))
+    # the reference multiplies a DENSIFIED matrix (dense fp32 GEMM order); same sums, other order
+    assert rel(ue, g["dhcf_user_out"]) < 1e-5 and rel(ie, g["dhcf_item_out"]) < 1e-5
