@@ -22,6 +22,7 @@ class CsrDesc(C.Structure):
         ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p),
         ("chunk_nnz", C.c_int32), ("n_heavy_rows", C.c_int32), ("n_chunks", C.c_int64),
         ("heavy_rows", C.c_void_p), ("heavy_chunk_ptr", C.c_void_p), ("chunk_owner", C.c_void_p),
+        ("work_order", C.c_void_p), ("n_work", C.c_int64),
     ]
 
 

@@ -231,7 +231,56 @@ __device__ __forceinline__ void finish_row(float4 acc, int64_t row, int gl, unsi
     }
 }
 
-// grid = [heavy chunk blocks | light row blocks]
+
+// What a row group works on.  Legacy layout (A.work_order == NULL): grid = [heavy chunk blocks | light row blocks] in
+// stored order.  With a work list, entry w >= 0 is a whole (unsplit) row, w < 0 is chunk ~w of the split plan; the host
+// orders the list (rows binned by length so that the two half-warps of a warp and the 16 groups of a block retire
+// together, chunk blocks interleaved with row blocks so the DRAM-bound and the L2-bound gathers overlap).  The order
+// only schedules: every row is still accumulated by ONE group in stored order, so no bit of the result depends on it.
+struct WorkItem {
+    int64_t s, e;    // nonzero range
+    int64_t target;  // row (kind 0) or chunk (kind 1); -1: nothing to do
+    int kind;
+};
+
+template <int GPB>
+__device__ __forceinline__ WorkItem resolve_work(const hgr_csr_t &A, int g, int heavy_blocks) {
+    WorkItem w;
+    w.s = w.e = 0;
+    w.target = -1;
+    w.kind = 0;
+    int64_t chunk = -1, row = -1;
+    if (A.work_order) {
+        const int64_t wi = (int64_t)blockIdx.x * GPB + g;
+        if (wi >= A.n_work) return w;
+        const int id = A.work_order[wi];
+        if (id < 0) chunk = (int64_t)(~id);
+        else row = id;
+    } else if ((int)blockIdx.x < heavy_blocks) {
+        chunk = (int64_t)blockIdx.x * GPB + g;
+        if (chunk >= A.n_chunks) return w;
+    } else {
+        row = (int64_t)(blockIdx.x - heavy_blocks) * GPB + g;
+        if (row >= A.n_rows) return w;
+    }
+    if (chunk >= 0) {
+        const int h = A.chunk_owner[chunk];
+        const int r = A.heavy_rows[h];
+        w.s = A.indptr[r] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
+        const int64_t row_end = A.indptr[r + 1];
+        w.e = w.s + A.chunk_nnz < row_end ? w.s + A.chunk_nnz : row_end;
+        w.target = chunk;
+        w.kind = 1;
+        return w;
+    }
+    w.s = A.indptr[row];
+    w.e = A.indptr[row + 1];
+    if (!A.work_order && A.n_heavy_rows > 0 && w.e - w.s > (int64_t)A.chunk_nnz) return w;  // summed by spmm_heavy_reduce_kernel
+    w.target = row;
+    return w;
+}
+
+// grid = [heavy chunk blocks | light row blocks], or the blocks of A.work_order
 template <int LPR, int UNR, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_kernel(hgr_csr_t A, const float4 *__restrict__ X4,
                                                              float *__restrict__ Y, hgr_epilogue_t ep,
@@ -240,24 +289,11 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_kernel(hgr_csr_t A, 
     const int gl = threadIdx.x % LPR;
     const int g = threadIdx.x / LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
-    if ((int)blockIdx.x < heavy_blocks) {
-        const int64_t chunk = (int64_t)blockIdx.x * GPB + g;
-        if (chunk >= A.n_chunks) return;
-        const int h = A.chunk_owner[chunk];
-        const int row = A.heavy_rows[h];
-        const int64_t s = A.indptr[row] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
-        const int64_t row_end = A.indptr[row + 1];
-        const int64_t e = s + A.chunk_nnz < row_end ? s + A.chunk_nnz : row_end;
-        const float4 acc = gather_accumulate<LPR, UNR>(A.indices, A.values, X4, s, e, gl, gmask);
-        partials[chunk * LPR + gl] = acc;
-        return;
-    }
-    const int64_t row = (int64_t)(blockIdx.x - heavy_blocks) * GPB + g;
-    if (row >= A.n_rows) return;
-    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
-    if (A.n_heavy_rows > 0 && e - s > (int64_t)A.chunk_nnz) return;  // summed by spmm_heavy_reduce_kernel
-    const float4 acc = gather_accumulate<LPR, UNR>(A.indices, A.values, X4, s, e, gl, gmask);
-    finish_row<LPR>(acc, row, gl, gmask, ep, Y);
+    const WorkItem w = resolve_work<GPB>(A, g, heavy_blocks);
+    if (w.target < 0) return;
+    const float4 acc = gather_accumulate<LPR, UNR>(A.indices, A.values, X4, w.s, w.e, gl, gmask);
+    if (w.kind) partials[w.target * LPR + gl] = acc;
+    else finish_row<LPR>(acc, w.target, gl, gmask, ep, Y);
 }
 
 template <int LPR, int HB, int MINB>
@@ -270,23 +306,11 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_async_kernel(hgr_csr
     const int g = threadIdx.x / LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
     float4 *ring = spmm_ring + threadIdx.x;
-    if ((int)blockIdx.x < heavy_blocks) {
-        const int64_t chunk = (int64_t)blockIdx.x * GPB + g;
-        if (chunk >= A.n_chunks) return;
-        const int h = A.chunk_owner[chunk];
-        const int row = A.heavy_rows[h];
-        const int64_t s = A.indptr[row] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
-        const int64_t row_end = A.indptr[row + 1];
-        const int64_t e = s + A.chunk_nnz < row_end ? s + A.chunk_nnz : row_end;
-        partials[chunk * LPR + gl] = gather_accumulate_async<LPR, HB>(A.indices, A.values, X4, s, e, gl, gmask, ring);
-        return;
-    }
-    const int64_t row = (int64_t)(blockIdx.x - heavy_blocks) * GPB + g;
-    if (row >= A.n_rows) return;
-    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
-    if (A.n_heavy_rows > 0 && e - s > (int64_t)A.chunk_nnz) return;
-    const float4 acc = gather_accumulate_async<LPR, HB>(A.indices, A.values, X4, s, e, gl, gmask, ring);
-    finish_row<LPR>(acc, row, gl, gmask, ep, Y);
+    const WorkItem w = resolve_work<GPB>(A, g, heavy_blocks);
+    if (w.target < 0) return;
+    const float4 acc = gather_accumulate_async<LPR, HB>(A.indices, A.values, X4, w.s, w.e, gl, gmask, ring);
+    if (w.kind) partials[w.target * LPR + gl] = acc;
+    else finish_row<LPR>(acc, w.target, gl, gmask, ep, Y);
 }
 
 // Sums the partial rows of the split rows and runs the epilogue.  A block takes GPB consecutive split rows.  Most of them
@@ -371,6 +395,10 @@ static int check_csr(const hgr_csr_t *A, const char *name) {
         HGR_REQUIRE(A->chunk_nnz > 0 && A->n_chunks > 0, "%s: split plan without chunk size", name);
         HGR_REQUIRE(A->heavy_rows && A->heavy_chunk_ptr && A->chunk_owner, "%s: NULL split-plan arrays", name);
     }
+    HGR_REQUIRE(A->n_work >= 0 && (A->work_order != nullptr || A->n_work == 0), "%s: n_work = %lld without a work list", name,
+                (long long)A->n_work);
+    if (A->work_order)
+        HGR_REQUIRE(A->n_work <= (int64_t)A->n_rows + A->n_chunks, "%s: work list longer than rows + chunks", name);
     return HGR_OK;
 }
 
@@ -393,9 +421,8 @@ template <int LPR, int UNR, int MINB>
 static int launch_spmm(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws,
                        cudaStream_t st) {
     constexpr int GPB = kThreads / LPR;
-    const int64_t heavy_blocks = A.n_heavy_rows > 0 ? ceil_div(A.n_chunks, GPB) : 0;
-    const int64_t light_blocks = ceil_div(A.n_rows, GPB);
-    const int64_t grid = heavy_blocks + light_blocks;
+    const int64_t heavy_blocks = A.work_order ? 0 : (A.n_heavy_rows > 0 ? ceil_div(A.n_chunks, GPB) : 0);
+    const int64_t grid = A.work_order ? ceil_div(A.n_work, GPB) : heavy_blocks + ceil_div(A.n_rows, GPB);
     if (grid == 0) return HGR_OK;
     HGR_REQUIRE(grid < (int64_t)0x7fffffff, "grid too large (%lld blocks)", (long long)grid);
     spmm_rows_kernel<LPR, UNR, MINB><<<(unsigned)grid, kThreads, 0, st>>>(A, reinterpret_cast<const float4 *>(X), Y, ep,
@@ -413,12 +440,22 @@ template <int LPR, int HB, int MINB>
 static int launch_spmm_async(const hgr_csr_t &A, const float *X, float *Y, const hgr_epilogue_t &ep, void *ws, cudaStream_t st) {
     constexpr int GPB = kThreads / LPR;
     float4 *partials = reinterpret_cast<float4 *>(ws);
-    const int64_t heavy_blocks = A.n_heavy_rows > 0 ? ceil_div(A.n_chunks, GPB) : 0;
-    const int64_t grid = heavy_blocks + ceil_div(A.n_rows, GPB);
+    const int64_t heavy_blocks = A.work_order ? 0 : (A.n_heavy_rows > 0 ? ceil_div(A.n_chunks, GPB) : 0);
+    const int64_t grid = A.work_order ? ceil_div(A.n_work, GPB) : heavy_blocks + ceil_div(A.n_rows, GPB);
     if (grid == 0) return HGR_OK;
     HGR_REQUIRE(grid < (int64_t)0x7fffffff, "grid too large (%lld blocks)", (long long)grid);
     const size_t smem = (size_t)2 * HB * kThreads * sizeof(float4);
-    HGR_CUDA_OK(cudaFuncSetAttribute(spmm_rows_async_kernel<LPR, HB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        // the attribute is per device: set it once for every device this process launches on
+        static std::atomic<uint64_t> done[2];  // bit d of done[d / 64]
+        int dev = 0;
+        HGR_CUDA_OK(cudaGetDevice(&dev));
+        const uint64_t bit = 1ull << (dev & 63);
+        if (dev >= 128 || !(done[(dev >> 6) & 1].load(std::memory_order_acquire) & bit)) {
+            HGR_CUDA_OK(cudaFuncSetAttribute(spmm_rows_async_kernel<LPR, HB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev < 128) done[(dev >> 6) & 1].fetch_or(bit, std::memory_order_release);
+        }
+    }
     spmm_rows_async_kernel<LPR, HB, MINB><<<(unsigned)grid, kThreads, smem, st>>>(A, reinterpret_cast<const float4 *>(X), Y, ep,
                                                                                  partials, (int)heavy_blocks);
     HGR_LAUNCH_OK("spmm_rows_async_kernel");

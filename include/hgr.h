@@ -62,6 +62,13 @@ typedef struct {
     const int32_t *heavy_rows;      /* [n_heavy_rows] */
     const int64_t *heavy_chunk_ptr; /* [n_heavy_rows + 1] */
     const int32_t *chunk_owner;     /* [n_chunks] */
+    /* Optional schedule of the propagation kernel: entry w >= 0 is unsplit row w, entry w < 0 is chunk ~w of the
+     * split plan; 16 consecutive entries (D = 64) share a thread block.  Every unsplit row and every chunk must
+     * appear exactly once.  graph.py bins rows by length and interleaves chunk blocks with row blocks; the order
+     * never changes a result bit (each row is still accumulated by one row group in stored order).
+     * NULL: rows in stored order, chunk blocks first. */
+    const int32_t *work_order; /* [n_work] or NULL */
+    int64_t n_work;
 } hgr_csr_t;
 
 /* Row-wise epilogue fused into the propagation kernel; applied to the accumulated row `acc` in

@@ -42,8 +42,8 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hgr.h"\nint main(void){\n'
-                   'printf("%zu %zu %zu %zu %zu\\n", sizeof(hgr_csr_t), offsetof(hgr_csr_t, chunk_nnz), offsetof(hgr_csr_t, chunk_owner),'
-                   ' offsetof(hgr_csr_t, indptr), offsetof(hgr_csr_t, n_chunks));\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hgr_csr_t), offsetof(hgr_csr_t, chunk_nnz), offsetof(hgr_csr_t, chunk_owner),'
+                   ' offsetof(hgr_csr_t, indptr), offsetof(hgr_csr_t, n_chunks), offsetof(hgr_csr_t, work_order), offsetof(hgr_csr_t, n_work));\n'
                    'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(hgr_epilogue_t), offsetof(hgr_epilogue_t, ln_gamma), offsetof(hgr_epilogue_t, residual),'
                    ' offsetof(hgr_epilogue_t, addends), offsetof(hgr_epilogue_t, scale), offsetof(hgr_epilogue_t, pre));\nreturn 0;}\n')
     exe = tmp_path / "layout"
@@ -52,7 +52,7 @@ def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
     a = [int(v) for v in out[0].split()]
     b = [int(v) for v in out[1].split()]
     d, e = lib.CsrDesc, lib.Epilogue
-    assert a == [C.sizeof(d), d.chunk_nnz.offset, d.chunk_owner.offset, d.indptr.offset, d.n_chunks.offset]
+    assert a == [C.sizeof(d), d.chunk_nnz.offset, d.chunk_owner.offset, d.indptr.offset, d.n_chunks.offset, d.work_order.offset, d.n_work.offset]
     assert b == [C.sizeof(e), e.ln_gamma.offset, e.residual.offset, e.addends.offset, e.scale.offset, e.pre.offset]
 
 
@@ -137,3 +137,33 @@ def test_shape_predicates_refuse_cpu_tensors_and_odd_widths():
 
     with pytest.raises(ValueError):
         ops.hyperedge(torch.ones(8, 128), torch.ones(8, 64))
+
+
+@pytest.mark.parametrize("mode", ["binned", "interleaved", "windowed", "windowed:7", "auto"])
+def test_work_schedule_lists_every_row_and_chunk_once(mode):
+    """hgr_csr_t::work_order: whatever the order, each unsplit row and each chunk of the split plan appears exactly once."""
+    import numpy as np
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200 import graph
+
+    rng = np.random.default_rng(5)
+    deg = np.concatenate([rng.integers(0, 40, 300), rng.integers(200, 900, 7), [0, 0, 1]])
+    rng.shuffle(deg)
+    indptr = np.zeros(deg.size + 1, dtype=np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    n_cols = 5000
+    indices = np.concatenate([np.sort(rng.choice(n_cols, d, replace=False)) for d in deg]).astype(np.int32)
+    chunk = 64
+    heavy, ptr, owner = graph.split_plan(indptr, chunk)
+    order = graph.work_schedule(torch.from_numpy(indptr), torch.from_numpy(heavy), int(owner.size), chunk, mode, torch.from_numpy(indices),
+                                torch.from_numpy(ptr), torch.from_numpy(owner), n_cols)
+    order = order.numpy()
+    rows = np.sort(order[order >= 0])
+    chunks = np.sort(~order[order < 0])
+    assert np.array_equal(rows, np.setdiff1d(np.arange(deg.size), heavy))
+    assert np.array_equal(chunks, np.arange(owner.size))
+    if mode == "binned":  # chunks first, then rows by descending length
+        r = order[order >= 0]
+        assert (order[: owner.size] < 0).all() and (np.diff(deg[r]) <= 0).all()
+    assert graph.work_schedule(torch.from_numpy(indptr), torch.from_numpy(heavy), int(owner.size), chunk, "stored") is None

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--rank", type=int, default=0)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--variants", default="0", help="hgr_set_spmm_variant values to time (include/hgr.h)")
+    ap.add_argument("--schedules", default="stored,binned,windowed", help="work schedules to time (graph.work_schedule)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     U, I, E = 1_250_000 * args.world, 250_000 * args.world, 125_000_000 * args.world
@@ -40,9 +41,10 @@ def main():
     x = torch.randn(part.n_glob, 64, device=dev)
     from hypergraph_diffusion_for_recommendation_b200 import _lib
 
-    for variant in (int(v) for v in args.variants.split(",")):
+    for sched, variant in ((s, int(v)) for s in args.schedules.split(",") for v in args.variants.split(",")):
+        block.set_schedule(sched)
         _lib.check(_lib.lib().hgr_set_spmm_variant(variant))
-        print("variant %d" % variant, flush=True)
+        print("schedule %s variant %d" % (sched, variant), flush=True)
         for _ in range(2):
             y = ops.spmm_raw(block, x)
         ts = []

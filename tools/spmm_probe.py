@@ -20,7 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="52000x92000x3000000,1250000x250000x125000000")
     ap.add_argument("--chunks", default="0")
-    ap.add_argument("--variants", default="5,0,6,7,8")
+    ap.add_argument("--variants", default="0")
+    ap.add_argument("--schedules", default="stored,binned,interleaved")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--d", type=int, default=64)
     args = ap.parse_args()
@@ -43,7 +44,10 @@ def main():
                 shape, nnz, t1 - t0, t2 - t1, adj.chunk_nnz, adj.desc.n_heavy_rows, adj.desc.n_chunks, int(deg.max())), flush=True)
             _lib.check(_lib.lib().hgr_set_spmm_variant(5))
             y_ref = ops.spmm_raw(adj, x).clone()
-            for variant in (int(v) for v in args.variants.split(",")):
+            adj.set_schedule("stored")
+            y_ref = ops.spmm_raw(adj, x).clone()
+            for sched, variant in ((s, int(v)) for s in args.schedules.split(",") for v in args.variants.split(",")):
+                adj.set_schedule(sched)
                 _lib.check(_lib.lib().hgr_set_spmm_variant(variant))
                 for _ in range(3):
                     y = ops.spmm_raw(adj, x)
@@ -60,8 +64,8 @@ def main():
                     times.append(s.elapsed_time(e))
                 ms = sorted(times)[len(times) // 2]
                 b = algorithmic_bytes(n, nnz, args.d)
-                print("  variant %d | spmm median %.3f ms min %.3f ms | alg %.1f MB -> %.0f GB/s | %.1f Gnnz/s" % (
-                    variant, ms, min(times), b / 1e6, b / ms / 1e6, nnz / ms / 1e6), flush=True)
+                print("  %-11s variant %d | spmm median %.3f ms min %.3f ms | alg %.1f MB -> %.0f GB/s | %.1f Gnnz/s" % (
+                    sched, variant, ms, min(times), b / 1e6, b / ms / 1e6, nnz / ms / 1e6), flush=True)
             del adj, x, y
 
 
