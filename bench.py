@@ -10,15 +10,21 @@ sampler yields CPU LongTensors and its loop calls ``.item()``, model/graph/Light
 Workloads (``--workload``; SURVEY.md section 8 shapes, synthetic power-law graphs, seed 1234):
   c5w (default)  BASELINE configs[4] weak-scaled: 1.25 M users x 0.25 M items x 125 M interactions PER GPU
                  (N = 8 is exactly the 10 M x 2 M x 1 B graph); inputs are larger than L2, no flush needed
-  c4 / c3 / c2   the named Amazon-Book / Gowalla / ml-1m shapes on one GPU; L2 is flushed between steps
+  c4 / c3 / c2   the named Amazon-Book / Gowalla / ml-1m shapes; L2 is flushed between steps.  The default run
+                 appends short legs of them under ``extra_configs`` (C4 hypergraph-diffusion, C3 HCCF, C2 LightGCN at
+                 N = 1; the C4 strong-scaling point at N > 1); they go through the data facade (``data.Interaction``).
 
-``--impl reference`` times the reference's own CPU torch path (oracle/torch_path.py, the same torch
-calls the reference makes) on the host cores, on a bounded sample of the same workload, and prints
-the same JSON line with "impl": "reference".
+N > 1 also runs ``dist_check.parity_check`` (sharded == NCCL-only == unsharded, sharded evaluation == unsharded) on the
+ranks of this very job and reports it as ``"parity"``.
+
+``--impl reference`` times the reference's own CPU torch path (oracle/torch_path.py, the same torch calls the reference
+makes, including its python sampler) on the host cores, on a bounded sample of the same workload, and prints the same JSON
+line with "impl": "reference".
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -46,15 +52,17 @@ WORKLOAD_NOTE = {
 }
 MODELS = {"hgnn_hd3": "HGNN_HD3 local encoder (EquivSetConv + HGCNConv), 2 layers", "lightgcn": "LightGCN, 3 layers",
           "hccf": "HCCF, 2 layers, 128 learned hyperedges, edge keep 0.8, contrastLoss on the batch's unique users/items (temp 0.2)"}
+SPMM_PER_STEP = {"hgnn_hd3": 12, "lightgcn": 6, "hccf": 4}
 HCCF_CONF = {"lrate": 0.001, "lr_decay": 1.0, "max_epoch": 1, "batch_size": 4096, "reg": 0.0, "embedding_size": 64, "hyper_dim": 128,
              "drop_rate": 0.2, "p": 0.5, "n_layers": 2}
 HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP = 0.2, 0.1, 0.8
 D = 64
 REG = 0.01
 LR = 0.001
-CPU_SAMPLE_DIV = {"c5w": 64, "c4": 1, "c3": 1, "c2": 1}
-# dram__bytes_read.sum + dram__bytes_write.sum of one spmm_rows_async_kernel launch (ncu --set full, profiles/spmm_r1.md)
-SPMM_DRAM_TRAFFIC = {("c5w", 1): 19.96e9, ("c4", 1): 99.8e6}
+# the CPU arm runs on 1 / CPU_SAMPLE_DIV of the workload (same power-law generator, same encoder, batch scaled alike)
+CPU_SAMPLE_DIV = {"c5w": 8, "c4": 1, "c3": 1, "c2": 1}
+EXTRA_LEGS = (("c4", "hgnn_hd3"), ("c3", "hccf"), ("c2", "lightgcn"))
+PROFILE_CACHE = os.path.join(ROOT, "profiles", "kernel_counters.json")
 
 
 def parse_args():
@@ -66,10 +74,11 @@ def parse_args():
     ap.add_argument("--workload", default="c5w", choices=sorted(WORKLOADS))
     ap.add_argument("--model", default="hgnn_hd3", choices=sorted(MODELS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs and the N > 1 parity check")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis: do not poll nvidia-smi during the timed region")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the training step as one CUDA graph (auto: single-GPU L2-resident workloads, not hccf)")
+                    help="replay the training step as one CUDA graph (auto: single-GPU L2-resident workloads)")
     return ap.parse_args()
 
 
@@ -78,8 +87,18 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return p, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def profile_counters(key):
+    """Hardware counters of one launch that cannot be read outside a profiler (DRAM bytes, tensor-pipe cycles): captured once
+    per shape with `tools/measure_counters.py` (ncu) and cached under profiles/kernel_counters.json, keyed by shape."""
+    try:
+        with open(PROFILE_CACHE) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
 
 
 def spmm_algorithmic_bytes(n_rows, n_cols, nnz, d):
@@ -150,14 +169,21 @@ def workload_dims(name, n_gpus):
     return u * k, i * k, e * k, b * k
 
 
+def workload_label(workload, model_name, n_gpus):
+    U, I, E, B = workload_dims(workload, n_gpus)
+    return "%s: %d users x %d items x %d interactions, emb %d, %s, batch %d" % (workload, U, I, E, D, MODELS[model_name], B)
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU torch path on a bounded sample
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
+    """The reference's training step (oracle/torch_path.py: its torch calls, its python sampler) on all host cores, on
+    1 / div of the workload.  Returns the MEASURED sample step time and the scaling rule separately."""
     import numpy as np
     import torch
 
-    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device
     from oracle import hgr_oracle as O
     from oracle import torch_path as T
 
@@ -166,9 +192,12 @@ def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
     U, I, E, B = workload_dims(workload, n_gpus)
     div = CPU_SAMPLE_DIV[workload] * (n_gpus if WORKLOADS[workload][4] else 1)
     su, si, se, sb = max(U // div, 64), max(I // div, 64), max(E // div, 1024), max(B // div, 256)
-    g = powerlaw_interactions(su, si, se, seed=1234)
-    csr = O.build_norm_adj(g.train_u, g.train_i, su, si)
+    t0 = time.perf_counter()
+    gu, gi = powerlaw_interactions_device(su, si, se, torch.device("cpu"), seed=1234)
+    train_u, train_i = gu.numpy().astype(np.int64), gi.numpy().astype(np.int64)
+    csr = O.build_norm_adj(train_u, train_i, su, si)
     adj = T.coo_from_csr(*csr, (su + si, su + si))
+    setup_s = time.perf_counter() - t0
     torch.manual_seed(1234)
     if model_name == "hccf":
         model = T.HCCF(adj, su, si, D, 128, 2)
@@ -178,41 +207,66 @@ def cpu_reference_run(workload, model_name, steps, warmup, n_gpus):
         model.eval()  # dropout off, like the GPU arm (the reference's loop leaves it off after the first batch)
     opt = torch.optim.Adam(model.parameters(), lr=LR)
     rng = np.random.default_rng(7)
-    times = []
+    # the reference's sampler (util/sampler.py:237-264): shuffled positives, one python-level rejection loop per sample.
+    # Its dict-of-dict training sets exist before the loop starts (Interaction.__init__), so the sets of the users the
+    # timed batches touch are built here, outside the timed region
+    picks = [rng.integers(0, train_u.size, sb) for _ in range(warmup + steps)]
+    order = np.argsort(train_u, kind="stable")
+    ptr = np.zeros(su + 1, dtype=np.int64)
+    np.cumsum(np.bincount(train_u, minlength=su), out=ptr[1:])
+    items_by_user = train_i[order]
+    sets = {}
+    for pick in picks:
+        for uu in np.unique(train_u[pick]).tolist():
+            if uu not in sets:
+                sets[uu] = set(items_by_user[ptr[uu]:ptr[uu + 1]].tolist())
+    item_list = list(range(si))
+    step_times, sampler_times = [], []
     for s in range(warmup + steps):
-        pick = rng.integers(0, g.train_u.size, sb)
-        u = torch.from_numpy(g.train_u[pick])
-        p = torch.from_numpy(g.train_i[pick])
-        n = torch.from_numpy(rng.integers(0, si, sb))
+        pick = picks[s]
         t0 = time.perf_counter()
+        u, p, n = T.sample_batch_pairwise(train_u[pick].tolist(), train_i[pick].tolist(), sets, item_list)
+        t1 = time.perf_counter()
         if model_name == "hccf":
             T.train_step_hccf(model, opt, u, p, n, HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP)
         else:
             T.train_step(model, opt, u, p, n, REG, sb)
+        t2 = time.perf_counter()
         if s >= warmup:
-            times.append(time.perf_counter() - t0)
-    step_s = sum(times) / len(times)
+            sampler_times.append(t1 - t0)
+            step_times.append(t2 - t0)
+    step_s = sum(step_times) / len(step_times)
     steps_per_epoch = math.ceil(E / B)
-    # work per step is proportional to nnz: scale the sampled step back to the full graph
+    # work per step (propagation over all nonzeros + a batch of triples) is proportional to the graph: the sample holds
+    # 1 / div of the interactions AND 1 / div of the batch, so one full-size step = div sampled steps
     epoch_s = step_s * div * steps_per_epoch
-    sample = "%d x %d x %d interactions (1/%d of the workload), batch %d, %d threads; step time x %d x %d steps/epoch" % (
-        su, si, se, div, sb, cores, div, steps_per_epoch)
-    return {"epoch_s": epoch_s, "step_ms_sample": step_s * 1e3, "cores": cores, "sample": sample, "div": div,
-            "nnz_per_s": 2 * se * {"hgnn_hd3": 12, "lightgcn": 6, "hccf": 4}[model_name] / step_s}
+    sample = "%d users x %d items x %d interactions (1/%d of the workload), batch %d, %d threads, %d timed steps" % (su, si, se, div, sb, cores, steps)
+    return {"epoch_s": epoch_s, "step_ms_sample": step_s * 1e3, "sampler_ms_sample": 1e3 * sum(sampler_times) / len(sampler_times),
+            "cores": cores, "sample": sample, "div": div, "steps_per_epoch": steps_per_epoch, "setup_s": setup_s,
+            "scaling_rule": "epoch_s = measured sample step (%.1f ms, of which the reference's python sampler %.1f ms) x %d (sample -> full graph and batch) x %d steps/epoch"
+                            % (step_s * 1e3, 1e3 * sum(sampler_times) / len(sampler_times), div, steps_per_epoch),
+            "nnz_per_s": 2 * se * SPMM_PER_STEP[model_name] / step_s}
+
+
+def cpu_baseline_block(r):
+    return {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+            "sample_step_ms": r["step_ms_sample"], "sample_sampler_ms": r["sampler_ms_sample"], "sample_fraction": 1.0 / r["div"],
+            "scaling_rule": r["scaling_rule"],
+            "why_port": "the reference is a Python script tree: /root/reference does not exist on the GPU box and it has no installable package; "
+                        "oracle/torch_path.py restates its torch call sequence and is pinned to its outputs by tests/test_oracle_golden.py"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.workload, args.model, max(1, min(args.steps, 3)), min(args.warmup, 1), args.gpus)
-    U, I, E, B = workload_dims(args.workload, args.gpus)
+    r = cpu_reference_run(args.workload, args.model, max(1, min(args.steps, 2)), min(args.warmup, 1), args.gpus)
     line = {
         "impl": "reference", "metric": "epoch_s", "value": r["epoch_s"], "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["step_ms_sample"] * r["div"], "higher_is_better": False,
         "scaling": "weak" if WORKLOADS[args.workload][4] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d users x %d items x %d interactions, emb %d, %s, batch %d" % (args.workload, U, I, E, D, MODELS[args.model], B)},
-        "cpu_baseline": {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "config": {"workload": workload_label(args.workload, args.model, args.gpus)},
+        "cpu_baseline": cpu_baseline_block(r),
         "e2e": {"value": r["epoch_s"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -221,7 +275,46 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Job:
+    """Process-wide state of one bench invocation (device, ranks)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run --nproc-per-node N)" % (args.gpus, self.world))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: libhgr.so has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from hypergraph_diffusion_for_recommendation_b200 import _lib
+
+        _lib.lib()
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def close(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.destroy_process_group()
+
+
+def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, primary):
+    """One workload on this job's GPUs; returns the JSON line (rank 0) or None."""
     import types
 
     import torch
@@ -230,50 +323,54 @@ def run_ours(args):
     from hypergraph_diffusion_for_recommendation_b200 import _lib, encoders, ops, trainer
     from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run --nproc-per-node N)" % (args.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libhgr.so has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()
-
-    U, I, E, B = workload_dims(args.workload, world)
-    small = not WORKLOADS[args.workload][4]
+    args, world, rank, dev = job.args, job.world, job.rank, job.dev
+    U, I, E, B = workload_dims(workload, world)
+    small = not WORKLOADS[workload][4]
     u, i = powerlaw_interactions_device(U, I, E, dev, seed=1234)
-    part, build_s = None, None
+    part, build_s, facade = None, None, None
+    torch.cuda.synchronize()
+    t_build = time.perf_counter()
     if world > 1:
         from hypergraph_diffusion_for_recommendation_b200 import dist as hdist
 
+        # every rank keeps the interactions that touch the rows it owns and builds its block of the normalised adjacency
         ctx = hdist.build_partitioned(u, i, U, I, rank, world, dev)
         data, adj, part = ctx.data, ctx.adj, ctx.part
+    elif small:
+        # the named configurations go through the data facade the reference's models read (data.Interaction: id maps,
+        # dict views, matrices from the device builder), like `SELFRec.__init__` -> `Interaction(conf, training, test)`
+        from hypergraph_diffusion_for_recommendation_b200 import data as hdata
+
+        tu, ti = heldout_pairs(u, i, U, I, dev)
+        facade = hdata.Interaction(None, hdata.InteractionList(u.cpu().numpy(), i.cpu().numpy() + U),
+                                   hdata.InteractionList(tu.cpu().numpy(), ti.cpu().numpy() + U), device=dev)
+        data = facade
+        adj = encoders._adjacency_of(data)
     else:
-        # the product builder (csrc/graph_build.cu: radix sort + dedup + LUT normalisation), timed: this is what replaces
+        # the product builder (csrc/graph_build.cu: radix sort + dedup + LUT normalisation): this is what replaces
         # Interaction.__create_sparse_bipartite_adjacency + normalize_graph_mat (data/ui_graph.py:70-84, data/graph.py:11-25)
         from hypergraph_diffusion_for_recommendation_b200 import graph as hgraph
 
-        torch.cuda.synchronize()
-        t_build = time.perf_counter()
         adj = hgraph.build_norm_adj(u, i, U, I, device=dev)
-        torch.cuda.synchronize()
-        build_s = time.perf_counter() - t_build
         data = types.SimpleNamespace(n_users=U, n_items=I, norm_adj=None, norm_adj_device=adj)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+    if facade is not None:
+        # dense ids in order of first appearance, like the reference numbers them: the training pairs in the facade's ids
+        pu, pi = facade.dense_training_pairs()
+        u, i = torch.as_tensor(pu).to(dev, torch.int32), torch.as_tensor(pi).to(dev, torch.int32)
+        U, I = int(facade.n_users), int(facade.n_items)
     nnz = int(adj._nnz())
     torch.manual_seed(1234)
-    if args.model == "hgnn_hd3":
+    if model_name == "hgnn_hd3":
         model = encoders.HGNNModel(data, {"hyper_dim": D, "n_layers": 2, "p": 0.3, "drop_rate": 0.2, "batch_size": B}).to(dev)
-    elif args.model == "hccf":
+    elif model_name == "hccf":
         if world > 1:
             raise SystemExit("--model hccf is a single-GPU workload (BASELINE configs[2])")
         model = encoders.HCCFEncoder(HCCF_CONF, data).to(dev)
     else:
         model = encoders.LGCN_Encoder(data, D, 3).to(dev)
-    if args.model == "hccf":
+    if model_name == "hccf":
         model.train()  # HCCF.train calls model.train() every batch (HCCF.py:81): dropout on the learned incidence stays on
     else:
         model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
@@ -289,37 +386,31 @@ def run_ours(args):
     sgen = torch.Generator(device=dev)
     sgen.manual_seed(1234)
     perm = torch.randperm(int(u.numel()), device=dev, generator=sgen)
-    n_steps = args.warmup + args.steps
+    n_steps = warmup + steps
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)  # the same batch on every rank: the sharded step evaluates the loss on the whole batch (dist.py)
     b_local = B
     host_triples, dev_triples = [], []
     for s in range(n_steps):
         pick = torch.randint(0, int(u.numel()), (b_local,), device=dev, generator=gen)
-        tu, tp = u[pick].to(torch.int64), i[pick].to(torch.int64)
-        tn = torch.randint(0, I, (b_local,), device=dev, generator=gen)
-        dev_triples.append((tu, tp, tn))
-        host_triples.append(tuple(t.cpu().pin_memory() for t in (tu, tp, tn)))
-    eval_inputs = build_eval_inputs(u, i, U, I, part, rank, dev)
+        tu_, tp_ = u[pick].to(torch.int64), i[pick].to(torch.int64)
+        tn_ = torch.randint(0, I, (b_local,), device=dev, generator=gen)
+        dev_triples.append((tu_, tp_, tn_))
+        host_triples.append(tuple(t.cpu().pin_memory() for t in (tu_, tp_, tn_)))
+    eval_inputs = build_eval_inputs(u, i, U, I, part, rank, dev) if primary or facade is None else None
     del u, i
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
 
     spmm_events = []
     ops.PROFILE_EVENTS = None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     graphed = None
     if use_graph:
         # warm-up (three Adam steps on an all-zero batch, off the default stream) and capture; the timed steps then replay the
         # graph on the real batches.  The warm-up steps nudge the parameters, which timing does not depend on
-        if args.model == "hccf":
+        if model_name == "hccf":
             # torch.unique's variable-length result is replaced by the fixed-size sorted-with-gaps form (loss_torch.unique_padded)
-            graphed = trainer.GraphedStep(lambda tu, tp, tn: trainer.train_step_hccf(model, optimizer, tu, tp, tn, HCCF_TEMP, HCCF_SS_RATE,
-                                                                                     HCCF_KEEP, static_shapes=True), b_local, dev)
+            graphed = trainer.GraphedStep(lambda a, b, c: trainer.train_step_hccf(model, optimizer, a, b, c, HCCF_TEMP, HCCF_SS_RATE,
+                                                                                  HCCF_KEEP, static_shapes=True), b_local, dev)
         else:
             graphed = trainer.GraphedTrainStep(model, optimizer, REG, B, b_local)
 
@@ -328,18 +419,18 @@ def run_ours(args):
             return graphed(tri[0], tri[1], tri[2])
         if world > 1:
             return hdist.train_step(model, optimizer, adj, tri[0], tri[1], tri[2], REG, B)
-        if args.model == "hccf":
+        if model_name == "hccf":
             return trainer.train_step_hccf(model, optimizer, tri[0], tri[1], tri[2], HCCF_TEMP, HCCF_SS_RATE, HCCF_KEEP)
         return trainer.train_step(model, optimizer, tri[0], tri[1], tri[2], REG, B)
 
     def timed(kind):
-        """K steps; returns (total ms over the timed steps as max over ranks, last losses)."""
+        """K steps; returns (total ms over the timed steps as max over ranks, last losses, launches)."""
         losses = None
-        for s in range(args.warmup):
+        for s in range(warmup):
             losses = step(dev_triples[s])
             if kind == "e2e":
                 losses.tolist()
-        barrier()
+        job.barrier()
         per_step = []
         launches0 = _lib.launch_count()
         ops.PROFILE_EVENTS = spmm_events if kind == "device" else None
@@ -347,7 +438,7 @@ def run_ours(args):
         t_end = torch.cuda.Event(enable_timing=True)
         if not small:
             t_start.record()
-        for s in range(args.warmup, n_steps):
+        for s in range(warmup, n_steps):
             if small:
                 flush.fill_(s & 0xff)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,7 +446,7 @@ def run_ours(args):
             if kind == "e2e":
                 tri = tuple(t.to(dev, non_blocking=True) for t in host_triples[s])
                 losses = step(tri)
-                host_losses = losses.tolist()  # D2H of the step's result, like the reference's .item() calls
+                losses.tolist()  # D2H of the step's result, like the reference's .item() calls
             else:
                 off = (s * B) % max(int(perm.numel()) - B, 1)
                 losses = step(sampler.batch(perm, off, min(B, int(perm.numel()))))
@@ -364,11 +455,11 @@ def run_ours(args):
                 per_step.append((e0, e1))
         if not small:
             t_end.record()
-        barrier()
+        job.barrier()
         ops.PROFILE_EVENTS = None
         launches = _lib.launch_count() - launches0
         if graphed is not None:  # kernels replayed from the captured graph do not pass through the library's host counter
-            launches += graphed.kernels_per_replay * args.steps
+            launches += graphed.kernels_per_replay * steps
         total = sum(a.elapsed_time(b) for a, b in per_step) if small else t_start.elapsed_time(t_end)
         if world > 1:
             t = torch.tensor([total], device=dev, dtype=torch.float64)
@@ -376,7 +467,7 @@ def run_ours(args):
             total = float(t.item())
         return total, losses, launches
 
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(job.local_rank)
     if not args.no_clocks:
         clocks.start()
     if world > 1:
@@ -387,23 +478,26 @@ def run_ours(args):
     exchange = None
     if world > 1:
         # per step: propagations whose all-gather rode on the kernel epilogue (peer stores) vs NCCL collectives
-        exchange = {"fused_gathers_per_step": adj.n_fused / (args.steps + args.warmup), "nccl_gathers_per_step": adj.n_collective / (args.steps + args.warmup),
-                    "copy_kernel_gathers_per_step": adj.n_published / (args.steps + args.warmup), "fused": bool(adj.fused)}
+        exchange = {"fused_gathers_per_step": adj.n_fused / n_steps, "nccl_gathers_per_step": adj.n_collective / n_steps,
+                    "copy_kernel_gathers_per_step": adj.n_published / n_steps, "fused": bool(adj.fused),
+                    "multicast": bool(getattr(adj, "multicast", False))}
         # where the sharded step spends its time on this rank (CUDA events between the phases, timed steps only)
         torch.cuda.synchronize()
         phases = {}
-        for marks in adj.phase_events[args.warmup:]:
+        for marks in adj.phase_events[warmup:]:
             for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
-                phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1) / args.steps
+                phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1) / steps
         exchange["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
         adj.phase_events = None
     e2e_ms, _, _ = timed("e2e")
-    eval_info = run_eval(model, eval_inputs, part, adj, world, rank, dev, barrier)
+    eval_info = run_eval(job, model, eval_inputs, part, adj, workload) if eval_inputs is not None else None
+    if facade is not None and not primary:
+        eval_info = run_eval_facade(job, model, facade)
 
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / steps
     steps_per_epoch = math.ceil(E / B)
     epoch_s = ms_per_step * steps_per_epoch / 1e3
-    e2e_epoch_s = e2e_ms / args.steps * steps_per_epoch / 1e3
+    e2e_epoch_s = e2e_ms / steps * steps_per_epoch / 1e3
 
     # roofline of the dominant kernel (spmm_rows_async_kernel + its partial-row reduce), timed live
     torch.cuda.synchronize()
@@ -417,55 +511,99 @@ def run_ours(args):
                 model()
         ops.PROFILE_EVENTS = None
         torch.cuda.synchronize()
+    n_launch = sum(c for _, _, c in spmm_events)
     spmm_total_ms = sum(a.elapsed_time(b) for a, b, _ in spmm_events)
-    spmm_ms = [spmm_total_ms / max(sum(c for _, _, c in spmm_events), 1)] * sum(c for _, _, c in spmm_events)
-    peak, peak_src = measured_peaks()
-    n_rows, n_cols = (adj.block if world > 1 else adj).shape  # the rank's block of rows when sharded
-    alg = spmm_algorithmic_bytes(n_rows, n_cols, nnz, D)
-    avg_ms = sum(spmm_ms) / max(len(spmm_ms), 1)
-    achieved = alg / (avg_ms * 1e-3) / 1e9 if spmm_ms else None
-    traffic = SPMM_DRAM_TRAFFIC.get((args.workload, world))
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": traffic,
-                # the same launch time against the bytes that really crossed the HBM interface (ncu capture of this kernel and shape)
-                "dram_gbs": traffic / (avg_ms * 1e-3) / 1e9 if traffic and spmm_ms else None,
-                "dram_frac": traffic / (avg_ms * 1e-3) / 1e9 / peak if traffic and spmm_ms else None, "kernel": "spmm_rows_async_kernel<16,4,5> (+ spmm_heavy_reduce_kernel)", "launch_ms": avg_ms,
-                "launches_timed": len(spmm_ms), "algorithmic_bytes": alg, "peak_source": peak_src,
-                "spmm_share_of_step": ((2 * len(spmm_ms) / 3 * avg_ms) / ms_per_step if graphed is not None else sum(spmm_ms) / total_ms) if spmm_ms else None,
-                "note": "algorithmic bytes charge one 256-B row per nonzero to HBM (SURVEY.md 8d); the power-law graph lets L2 absorb "
-                        "about two thirds of that (traffic = dram bytes per launch from ncu, profiles/spmm_r1.md), so achieved can exceed the "
-                        "copy peak; ncu: 66.9 GB from L2 to the SMs in 6.0 ms = 5 940 B/clk, ~94 % of the ~6 300 B/clk L2-slice cap; DRAM at 51 % of the copy peak"}
+    avg_ms = spmm_total_ms / max(n_launch, 1)
+    block = adj.block if world > 1 else adj  # the rank's block of rows when sharded
+    roofline = spmm_roofline(workload, world, block, nnz, avg_ms, n_launch, ms_per_step, total_ms, graphed is not None, model_name)
 
+    line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
-            r = cpu_reference_run(args.workload, args.model, args.cpu_steps, 1, world)
-            cpu = {"value": r["epoch_s"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        if want_cpu:
+            cpu = cpu_baseline_block(cpu_reference_run(workload, model_name, cpu_steps, 1, world))
         line = {
-            "metric": "epoch_s", "value": epoch_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if WORKLOADS[args.workload][4] else "strong",
+            "metric": "epoch_s", "value": epoch_s, "unit": "s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if WORKLOADS[workload][4] else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: %d users x %d items x %d interactions, emb %d, %s, batch %d" % (args.workload, U, I, E, D, MODELS[args.model], B),
-                       "baseline_config": WORKLOAD_NOTE[args.workload],
+            "config": {"workload": workload_label(workload, model_name, world),
+                       "baseline_config": WORKLOAD_NOTE[workload],
                        "steps_per_epoch": steps_per_epoch, "nnz": nnz,
                        "l2": "flushed between steps (256 MiB write)" if small else "inputs larger than L2 (CSR %.1f GB + tables %.2f GB)" % (nnz * 8 / 1e9, (U + I) * D * 4 / 1e9),
-                       "cuda_graph": bool(use_graph),
-                       "parallelism": "1 GPU" if world == 1 else "row-partitioned x%d, NCCL all-gather per propagation" % world},
+                       "cuda_graph": bool(use_graph), "propagation_schedule": getattr(block, "schedule", None),
+                       "data_path": "data.Interaction facade" if facade is not None else "device builder on the raw pair list",
+                       "parallelism": "1 GPU" if world == 1 else "row-partitioned x%d, all-gather fused into the propagation epilogue" % world},
             "e2e": {"value": e2e_epoch_s, "unit": "s", "h2d_bytes_per_step": 3 * 8 * b_local, "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / steps},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
             "eval": eval_info, "exchange": exchange,
-            "graph_build": None if build_s is None else {"seconds": build_s, "interactions": E, "nnz": nnz,
-                                                         "what": "device COO -> normalised CSR + split plan (graph.build_norm_adj), one synchronisation"},
+            "graph_build": {"seconds": build_s, "interactions": E, "nnz": nnz,
+                            "what": ("this rank's block from the interactions of its own rows (dist.build_partitioned)" if world > 1 else
+                                     "data.Interaction: id maps + normalised CSR on the device" if facade is not None else
+                                     "device COO -> normalised CSR + split plan + work schedule (graph.build_norm_adj)")},
             "loss": [float(x) for x in losses.tolist()],
         }
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    del model, optimizer, sampler, adj, data, graphed, dev_triples, host_triples, eval_inputs, flush
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def spmm_roofline(workload, world, block, nnz, avg_ms, n_launch, ms_per_step, total_ms, graphed, model_name):
+    """The dominant kernel against the HBM roofline.  ``frac`` is the DRAM-side fraction: bytes that crossed the HBM interface
+    in one launch (ncu ``dram__bytes_read.sum + dram__bytes_write.sum`` of this kernel on this shape and schedule, cached in
+    profiles/kernel_counters.json by tools/measure_counters.py) / the launch time measured live / the measured copy peak.
+    The SURVEY 8(d) algorithmic figure charges one 256-byte row per nonzero to HBM although L2 serves most of them; it is kept
+    as ``algorithmic`` and is not a fraction of anything.  ``l2_to_sm`` compares the gathered bytes per second with the
+    random-row ceiling measured on this GPU model by tools/gather_probe.py (profiles/gather_probe_r2.txt)."""
+    peaks, peak_src = measured_peaks()
+    peak = float(peaks["hbm_gbs"])
+    n_rows, n_cols = block.shape
+    alg = spmm_algorithmic_bytes(n_rows, n_cols, nnz, D)
+    sched = getattr(block, "schedule", "stored")
+    key = "spmm:%s:%d:%s" % (workload, world, sched)
+    ctr = profile_counters(key)
+    traffic = (ctr["dram_read_bytes"] + ctr["dram_write_bytes"]) if ctr else None
+    sec = avg_ms * 1e-3
+    have = n_launch > 0 and sec > 0
+    dram_gbs = traffic / sec / 1e9 if traffic and have else None
+    gathered = 4 * D * nnz  # bytes the SMs pull out of L2 for the row gathers (ncu l1tex__m_xbar2l1tex_read_bytes agrees to 1 %)
+    ceiling = 18170.0       # GB/s: 250 M random 256-byte rows from an L2-resident table, profiles/gather_probe_r2.txt
+    share = None
+    if have:
+        share = (2 * n_launch / 3 * avg_ms) / ms_per_step if graphed else (n_launch * avg_ms) / total_ms
+    return {"bound": "hbm", "achieved": dram_gbs, "peak": peak, "unit": "GB/s", "frac": dram_gbs / peak if dram_gbs else None,
+            "traffic": traffic, "traffic_source": (ctr or {}).get("source") if ctr else "no ncu capture cached for %s" % key,
+            "kernel": "spmm_rows_async_kernel<16,4,5> (+ spmm_heavy_reduce_kernel), schedule %s" % sched,
+            "launch_ms": avg_ms if have else None, "launches_timed": n_launch, "peak_source": peak_src,
+            "spmm_share_of_step": share,
+            "algorithmic": {"bytes": alg, "gbs": alg / sec / 1e9 if have else None,
+                            "note": "SURVEY.md 8(d) formula: one 256-B row per nonzero charged to HBM; L2 serves most of them, so this is not an HBM rate"},
+            "l2_to_sm": {"bytes": gathered, "gbs": gathered / sec / 1e9 if have else None, "ceiling_gbs": ceiling,
+                         "frac": gathered / sec / 1e9 / ceiling if have else None,
+                         "ceiling_source": "tools/gather_probe.py: pure random 256-byte row gather from a 64 MB table (profiles/gather_probe_r2.txt)"},
+            "compulsory_bytes": 8 * (n_rows + 1) + 8 * nnz + 4 * D * (n_rows + n_cols),
+            "note": "the kernel is bound by gather delivery (L2 -> SM, L1TEX), not by HBM: its compulsory HBM bytes take < 10 % of the launch at the "
+                    "HBM peak and the DRAM-side fraction falls as the schedule improves L2 reuse (profiles/spmm_r2.md)"}
 
 
 EVAL_K = 20
 EVAL_MAX_USERS = 262_144  # test users ranked per GPU in the bench (all of them when the shape has fewer)
+
+
+def heldout_pairs(u, i, U, I, dev):
+    """Held-out interactions: fresh draws from the generator's distribution that are not training pairs (the reference's
+    75 / 25 split, dataset_util.py:20-37)."""
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device
+
+    n_draw = max(int(u.numel()) // 3, 1024)
+    tu, ti = powerlaw_interactions_device(U, I, n_draw, dev, seed=4321, cover=False, perm_seed=1234)
+    key = torch.sort(u.to(torch.int64) * I + i.to(torch.int64)).values
+    tkey = torch.unique(tu.to(torch.int64) * I + ti.to(torch.int64))
+    tkey = tkey[~torch.isin(tkey, key)]
+    return torch.div(tkey, I, rounding_mode="floor").to(torch.int32), (tkey % I).to(torch.int32)
 
 
 def build_eval_inputs(u, i, U, I, part, rank, dev):
@@ -478,22 +616,31 @@ def build_eval_inputs(u, i, U, I, part, rank, dev):
     key = torch.sort((u[m].to(torch.int64) - u0) * I + i[m].to(torch.int64)).values
     indptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
     torch.cumsum(torch.bincount(torch.div(key, I, rounding_mode="floor"), minlength=n_own), 0, out=indptr[1:])
-    # held-out interactions of the same users: fresh draws from the generator's distribution that are not training pairs
-    # (the reference's 75 / 25 split, dataset_util.py:20-37), as CSR for the metric code
-    from hypergraph_diffusion_for_recommendation_b200.synth import powerlaw_interactions_device
-
-    n_draw = max(int(u.numel()) // 3, 1024)
-    tu, ti = powerlaw_interactions_device(U, I, n_draw, dev, seed=4321, cover=False, perm_seed=1234)
+    tu, ti = heldout_pairs(u, i, U, I, dev)
     tm = (tu >= u0) & (tu < u0 + n_own)
-    tkey = torch.unique((tu[tm].to(torch.int64) - u0) * I + ti[tm].to(torch.int64))
-    tkey = tkey[~torch.isin(tkey, key)]
+    tkey = (tu[tm].to(torch.int64) - u0) * I + ti[tm].to(torch.int64)
     tptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
     torch.cumsum(torch.bincount(torch.div(tkey, I, rounding_mode="floor"), minlength=n_own), 0, out=tptr[1:])
     return {"n_own": n_own, "indptr": indptr, "indices": (key % I).to(torch.int32), "n_items": I,
             "truth_indptr": tptr.cpu().numpy(), "truth_items": (tkey % I).cpu().numpy()}
 
 
-def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
+def eval_roofline(workload, world, n_users_total, n_items, ms):
+    """Full-rank evaluation against the tensor roofline: the score contraction issues 3 bf16 MMAs per useful product (hi x hi,
+    hi x lo, lo x hi split operands), over all item tiles in the FILTER pass and a quarter of them in the SAMPLE pass.  ``achieved`` counts the ISSUED tensor flops of the whole
+    call (packing, thresholds and exact re-scoring included in the time); ``pipe_pct_elapsed`` is ncu's
+    sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed of the scoring kernels (cached capture)."""
+    peaks, src = measured_peaks()
+    peak = float(peaks.get("bf16_tflops", 1590.0)) * world
+    issued = 2.0 * D * n_items * n_users_total * 3 * 1.25  # FILTER pass over all tiles + SAMPLE pass over 1/4 of them
+    tf = issued / (ms * 1e-3) / 1e12
+    ctr = profile_counters("eval:%s:%d" % (workload, world)) or profile_counters("eval:%s:1" % workload)
+    return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_source": src,
+            "useful_tflops": tf / 3.75, "what": "issued bf16 MMA flops of both scoring passes / whole-call time (pack + score + threshold + exact re-score + D2H)",
+            "pipe_pct_elapsed": ctr, "traffic": None}
+
+
+def run_eval(job, model, ev, part, adj, workload, iters=3):
     """Full-ranking evaluation sharded by user: every rank ranks its own users against the whole item table
     (gathered once), top-EVAL_K with the training items masked.  users/s = users of all ranks / max time."""
     import numpy as np
@@ -502,6 +649,7 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
 
     from hypergraph_diffusion_for_recommendation_b200 import evaluation as E
 
+    world, dev = job.world, job.dev
     with torch.no_grad():
         out_u, out_i = model()[:2]
         users = torch.arange(ev["n_own"], device=dev, dtype=torch.int32)
@@ -519,7 +667,7 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
                                        return_stats=True)
         times, stats = [], None
         for it in range(iters + 1):
-            barrier()
+            job.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             ids, sc, stats = rank_all()
@@ -542,19 +690,92 @@ def run_eval(model, ev, part, adj, world, rank, dev, barrier, iters=3):
         sel = np.nonzero(has)[0]
         ptr = np.zeros(sel.size + 1, dtype=np.int64)
         np.cumsum(np.diff(ev["truth_indptr"])[sel], out=ptr[1:])
+        keep = np.repeat(has, np.diff(ev["truth_indptr"]))
+        torch.cuda.synchronize()
         t_m = time.perf_counter()
-        measures = E.ranking_evaluation_device(ptr, ev["truth_items"], ids[torch.from_numpy(sel).to(dev)], [EVAL_K]) if sel.size else []
+        measures = E.ranking_evaluation_device(ptr, ev["truth_items"][keep], ids[torch.from_numpy(sel).to(dev)], [EVAL_K]) if sel.size else []
+        torch.cuda.synchronize()
         measure_s = time.perf_counter() - t_m
         s = stats.tolist()
         flops = 2.0 * D * ev["n_items"] * n_users_total
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         tf = flops / (ms * 1e-3) / 1e12
         return {"users_per_s": n_users_total / ms * 1e3, "ms": ms, "users": n_users_total, "items": ev["n_items"], "k": EVAL_K,
                 "mode": "exact", "d2h_bytes": int(host_ids.numel() * 4), "score_tflops": tf,
-                "tensor_frac_of_measured_bf16": tf / (peaks.get("bf16_tflops", 1590.0) * world),
+                "roofline": eval_roofline(workload, world, n_users_total, ev["n_items"], ms),
                 "candidates_per_user": s[0] / max(ev["n_own"], 1), "rescored_per_user": s[1] / max(ev["n_own"], 1),
                 "fallback_users": s[2], "tensor_error_ppm_of_bound": s[3], "metrics_rank0": [m.strip() for m in measures], "metrics_users_rank0": int(sel.size),
                 "metrics_s": measure_s}
+
+
+def run_eval_facade(job, model, facade, iters=3):
+    """The reference's evaluation call on the facade: ``GraphRecommender.test`` body (evaluation.test -> rec_list dict) and
+    ``ranking_evaluation`` on ``data.test_set``, timed like ``base/graph_recommender.py:120-125`` times it."""
+    import types
+
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200 import evaluation as E
+
+    with torch.no_grad():
+        out_u, out_i = model()[:2]
+        rec = types.SimpleNamespace(data=facade, max_N=EVAL_K)
+        times = []
+        for it in range(iters + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ev = E.EvalData(facade, device=job.dev) if getattr(rec, "_hgr_eval_data", None) is None else rec._hgr_eval_data
+            rec._hgr_eval_data = ev
+            ids, sc = E.fullrank_topk(out_u.contiguous(), out_i.contiguous(), ev.test_users, ev.train_indptr, ev.train_indices, EVAL_K,
+                                      mode="refquirk")
+            ids.cpu()
+            torch.cuda.synchronize()
+            if it > 0:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        t_m = time.perf_counter()
+        measures = E.ranking_evaluation_device(ev.truth_indptr, ev.truth_items, ids, [EVAL_K])
+        measure_s = time.perf_counter() - t_m
+        n = int(ev.test_users.numel())
+        return {"users_per_s": n / ms * 1e3, "ms": ms, "users": n, "items": int(facade.n_items), "k": EVAL_K, "mode": "refquirk",
+                "metrics": [m.strip() for m in measures], "metrics_s": measure_s,
+                "roofline": eval_roofline("facade", 1, n, int(facade.n_items), ms)}
+
+
+def summarise(line):
+    """An extra_configs entry: the contract keys of one leg without the long notes."""
+    keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config",
+            "e2e", "gpu_launches", "clocks", "cpu_baseline", "eval", "exchange", "graph_build", "loss")
+    out = {k: line[k] for k in keep if k in line}
+    r = line.get("roofline") or {}
+    out["roofline"] = {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "launch_ms", "launches_timed", "spmm_share_of_step")}
+    out["roofline"]["l2_to_sm_gbs"] = (r.get("l2_to_sm") or {}).get("gbs")
+    return out
+
+
+def run_ours(args):
+    import torch
+
+    job = Job(args)
+    line = measure(job, args.workload, args.model, args.steps, args.warmup, args.cpu_steps, not args.no_cpu_baseline, primary=True)
+    if not args.no_extra and args.workload == "c5w":
+        extras = []
+        legs = EXTRA_LEGS if job.world == 1 else (("c4", "hgnn_hd3"),)
+        for wl, mdl in legs:
+            ex = measure(job, wl, mdl, min(args.steps, 10), max(3, min(args.warmup, 5)), 1, not args.no_cpu_baseline, primary=False)
+            if ex is not None:
+                extras.append(summarise(ex))
+        parity = None
+        if job.world > 1:
+            from hypergraph_diffusion_for_recommendation_b200 import dist_check
+
+            parity = dist_check.parity_check(job.rank, job.world, job.dev)
+        if line is not None:
+            line["extra_configs"] = extras
+            line["parity"] = parity
+    if line is not None:
+        emit(line)
+    torch.cuda.synchronize()
+    job.close()
 
 
 _JSON_FD = None

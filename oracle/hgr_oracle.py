@@ -169,6 +169,20 @@ def spmm(indptr, indices, data, x):
     return y
 
 
+def spmm_f64(indptr, indices, data, x):
+    """The same product accumulated in float64 (numpy), rounded once: the value both the reference's sequential fp32 chain
+    and any other fp32 summation order approximate.  Used by the parity tests for rows with 10^5 .. 10^6 nonzeros, where the
+    sequential fp32 chain of ``torch.sparse.mm`` is itself further than 1e-5 from the exact sum."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    out = np.zeros((indptr.size - 1, x.shape[1]), dtype=np.float64)
+    for r in range(indptr.size - 1):
+        s, e = int(indptr[r]), int(indptr[r + 1])
+        for b in range(s, e, 1 << 18):  # blocks bound the gathered temporary (2^18 x D doubles)
+            t = min(e, b + (1 << 18))
+            out[r] += np.asarray(data[b:t], dtype=np.float64) @ np.asarray(x[np.asarray(indices[b:t])], dtype=np.float64)
+    return out
+
+
 def lgcn_forward(csr, user_emb, item_emb, n_layers):
     """``LGCN_Encoder.forward`` (model/graph/LightGCN.py:129-140): L propagations, then the mean of
     the L+1 layer outputs (torch.mean over a stacked [N, L+1, D] tensor)."""

@@ -17,6 +17,7 @@ Call sites restated (paths relative to /root/reference/HD_SELFRec):
   util/loss_torch.py:5-9,17-21      bpr_loss, l2_reg_loss
   model/graph/LightGCN.py:49-66     one training step (forward, losses, .item() x3, backward, Adam)
   base/graph_recommender.py:61-92   test(): per-user GEMV, train-item mask, find_k_largest
+  util/sampler.py:237-264           next_batch_pairwise: per-sample python rejection loop over random.choice
 """
 from __future__ import annotations
 
@@ -225,3 +226,23 @@ def evaluate_users(user_emb, item_emb, test_users, train_indptr, train_indices, 
             cand[it] = -10e8
         rec[r], _ = O.find_k_largest(max_n, cand)
     return rec
+
+
+def sample_batch_pairwise(users, items, training_set_u, item_list, n_negs=1, choice=None):
+    """The per-batch body of ``next_batch_pairwise`` (util/sampler.py:248-263): for every positive pair one python-level
+    ``random.choice(item_list)`` redrawn while the item is in the user's training set, then three ``torch.LongTensor``s.
+    ``training_set_u[user]`` is any container with hash membership (the reference holds dicts); ids are already dense."""
+    import random
+
+    choice = choice or random.choice
+    u_idx, i_idx, j_idx = [], [], []
+    for k, user in enumerate(users):
+        i_idx.append(items[k])
+        u_idx.append(user)
+        seen = training_set_u[user]
+        for _ in range(n_negs):
+            neg_item = choice(item_list)
+            while neg_item in seen:
+                neg_item = choice(item_list)
+            j_idx.append(neg_item)
+    return torch.LongTensor(u_idx), torch.LongTensor(i_idx), torch.LongTensor(j_idx)

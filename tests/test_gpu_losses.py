@@ -9,10 +9,8 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # north_star tolerance for losses in fp32
 
 
-def rel_err(a, b):
-    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
-    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
-    return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), 1e-30)
+from conftest import global_rel_err as grad_err  # noqa: E402  gradients: relative to the largest row (see conftest)
+from conftest import rowwise_rel_err as rel_err  # noqa: E402  losses / forward values
 
 
 @pytest.fixture(scope="module")
@@ -30,10 +28,10 @@ def test_bpr_l2_matches_reference_losses_and_gradients(L, golden):
     rec, reg = L.bpr_l2_from_tables(ut, it, u, p, n, float(golden["loss_reg_lambda"]), int(golden["loss_reg_batch_size"]))
     assert rel_err(rec, golden["loss_bpr"]) < RTOL and rel_err(reg, golden["loss_reg"]) < RTOL
     (rec + reg).backward()
-    assert rel_err(ut.grad, golden["loss_dU"]) < RTOL and rel_err(it.grad, golden["loss_dI"]) < RTOL
+    assert grad_err(ut.grad, golden["loss_dU"]) < RTOL and grad_err(it.grad, golden["loss_dI"]) < RTOL
     o_rec, o_reg, o_du, o_di = O.bpr_l2_from_tables(golden["loss_user_tab"], golden["loss_item_tab"], golden["tri_u"], golden["tri_p"],
                                                     golden["tri_n"], float(golden["loss_reg_lambda"]), int(golden["loss_reg_batch_size"]))
-    assert rel_err(rec, o_rec) < RTOL and rel_err(ut.grad, o_du) < RTOL and rel_err(it.grad, o_di) < RTOL
+    assert rel_err(rec, o_rec) < RTOL and grad_err(ut.grad, o_du) < RTOL and grad_err(it.grad, o_di) < RTOL
 
 
 @pytest.mark.parametrize("d,batch", [(32, 1), (64, 4097), (128, 300)])
@@ -50,7 +48,7 @@ def test_bpr_l2_shapes_against_oracle(L, d, batch):
     # the oracle returns d(rec + reg); rebuild the weighted gradient from two oracle calls
     _, _, du0, di0 = O.bpr_l2_from_tables(ut, it, u, p, n, 0.0, 2048)  # d rec
     want_du, want_di = 2.0 * du0 + 3.0 * (o_du - du0), 2.0 * di0 + 3.0 * (o_di - di0)
-    assert rel_err(tu.grad, want_du) < 2e-5 and rel_err(ti.grad, want_di) < 2e-5
+    assert grad_err(tu.grad, want_du) < 2e-5 and grad_err(ti.grad, want_di) < 2e-5
 
 
 def test_reference_signature_bpr_loss_and_bad_indices(L, golden):
@@ -70,13 +68,13 @@ def test_contrast_loss_and_infonce_match_reference_golden(L, golden):
     loss = L.contrastLoss(e1, e2, torch.from_numpy(golden["cl_nodes"]), float(golden["cl_temp"]))
     assert rel_err(loss, golden["cl_loss"]) < RTOL
     loss.backward()
-    assert rel_err(e1.grad, golden["cl_d1"]) < 5e-5 and rel_err(e2.grad, golden["cl_d2"]) < 5e-5
+    assert grad_err(e1.grad, golden["cl_d1"]) < 5e-5 and grad_err(e2.grad, golden["cl_d2"]) < 5e-5
     v1 = torch.from_numpy(golden["nce_v1"]).cuda().requires_grad_(True)
     v2 = torch.from_numpy(golden["nce_v2"]).cuda().requires_grad_(True)
     loss = L.InfoNCE(v1, v2, float(golden["nce_temp"]))
     assert rel_err(loss, golden["nce_loss"]) < RTOL
     loss.backward()
-    assert rel_err(v1.grad, golden["nce_d1"]) < 5e-5 and rel_err(v2.grad, golden["nce_d2"]) < 5e-5
+    assert grad_err(v1.grad, golden["nce_d1"]) < 5e-5 and grad_err(v2.grad, golden["nce_d2"]) < 5e-5
 
 
 @pytest.mark.parametrize("d,n_rows,m", [(32, 40, 1), (64, 3000, 1111), (64, 5000, 4096), (128, 700, 65)])
@@ -95,7 +93,7 @@ def test_contrast_loss_shapes_against_oracle_and_torch(L, d, n_rows, m):
         assert abs(float(loss.detach()) - float(o_loss)) < 1e-6 and float(t1.grad.abs().max()) < 1e-6
         return
     assert rel_err(loss, o_loss) < RTOL
-    assert rel_err(t1.grad, 3.0 * o_d1) < 5e-5 and rel_err(t2.grad, 3.0 * o_d2) < 5e-5
+    assert grad_err(t1.grad, 3.0 * o_d1) < 5e-5 and grad_err(t2.grad, 3.0 * o_d2) < 5e-5
     # the reference's own expression in torch on the GPU (util/loss_torch.py:103-110), HCCF-style detached first view
     r1, r2 = torch.from_numpy(e1).cuda(), torch.from_numpy(e2).cuda().requires_grad_(True)
     a, b = F.normalize(r1 + 1e-8, p=2)[nodes], F.normalize(r2 + 1e-8, p=2)[nodes]
@@ -104,7 +102,7 @@ def test_contrast_loss_shapes_against_oracle_and_torch(L, d, n_rows, m):
     d2 = torch.from_numpy(e2).cuda().requires_grad_(True)
     got = L.contrastLoss(torch.from_numpy(e1).cuda(), d2, torch.from_numpy(nodes), 0.2)  # CPU index tensor, detached e1
     got.backward()
-    assert rel_err(got, ref) < RTOL and rel_err(d2.grad, r2.grad) < 5e-5
+    assert rel_err(got, ref) < RTOL and grad_err(d2.grad, r2.grad) < 5e-5
 
 
 @pytest.mark.parametrize("b_cos", [True, False])
@@ -123,10 +121,10 @@ def test_infonce_against_torch_expression(L, b_cos):
     ttl = torch.exp(a @ b.T / 0.2).sum(1)
     ref = (-torch.log(pos / ttl + 10e-6)).mean()
     ref.backward()
-    assert rel_err(loss, ref) < RTOL and rel_err(t1.grad, r1.grad) < 5e-5 and rel_err(t2.grad, r2.grad) < 5e-5
+    assert rel_err(loss, ref) < RTOL and grad_err(t1.grad, r1.grad) < 5e-5 and grad_err(t2.grad, r2.grad) < 5e-5
     if b_cos:
         o_loss, o_d1, o_d2 = O.info_nce(v1, v2, 0.2)
-        assert rel_err(loss, o_loss) < RTOL and rel_err(t1.grad, o_d1) < 5e-5
+        assert rel_err(loss, o_loss) < RTOL and grad_err(t1.grad, o_d1) < 5e-5
 
 
 @pytest.mark.parametrize("batch,n_rows", [(1, 50), (700, 300), (4096, 3000)])
@@ -151,9 +149,9 @@ def test_contrast_loss_padded_batch_equals_unique(L, batch, n_rows):
         assert abs(float(lp) - float(lu)) < 1e-6
         return
     assert rel_err(lp, lu) < 1e-6  # same terms, tiles cut differently
-    assert rel_err(a1.grad, b1.grad) < 1e-5 and rel_err(a2.grad, b2.grad) < 1e-5
+    assert grad_err(a1.grad, b1.grad) < 1e-5 and grad_err(a2.grad, b2.grad) < 1e-5
     o_loss, o_d1, o_d2 = O.contrast_loss(e1, e2, uniq, 0.2)
-    assert rel_err(lp, o_loss) < RTOL and rel_err(a1.grad, 2.0 * o_d1) < 5e-5 and rel_err(a2.grad, 2.0 * o_d2) < 5e-5
+    assert rel_err(lp, o_loss) < RTOL and grad_err(a1.grad, 2.0 * o_d1) < 5e-5 and grad_err(a2.grad, 2.0 * o_d2) < 5e-5
     touched = np.zeros(n_rows, dtype=bool)
     touched[uniq] = True
     assert not a1.grad[torch.from_numpy(~touched).cuda()].any()  # rows outside the batch get no gradient

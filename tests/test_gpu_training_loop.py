@@ -15,9 +15,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def rel(a, b):
-    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
-    return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / np.abs(b).max()
+from conftest import rowwise_rel_err as rel  # noqa: E402  row-wise: each embedding row against its own magnitude
 
 
 def test_lightgcn_trajectory_matches_the_reference():
@@ -57,6 +55,13 @@ def test_lightgcn_trajectory_matches_the_reference():
         assert rel(model.embedding_dict["user_emb"], g["epoch%d_user_param" % epoch]) < 1e-4
         assert rel(model.embedding_dict["item_emb"], g["epoch%d_item_param" % epoch]) < 1e-4
         assert rel(ue, g["epoch%d_user_emb" % epoch]) < 1e-4 and rel(ie, g["epoch%d_item_emb" % epoch]) < 1e-4
+        # the FORWARD pass on the reference's own parameters of this epoch: 1e-5 row-wise (north_star), no optimiser in between
+        probe = encoders.LGCN_Encoder(data, emb, layers).cuda()
+        with torch.no_grad():
+            probe.embedding_dict["user_emb"].copy_(torch.from_numpy(g["epoch%d_user_param" % epoch]))
+            probe.embedding_dict["item_emb"].copy_(torch.from_numpy(g["epoch%d_item_param" % epoch]))
+            pu, pi = probe()
+        assert rel(pu, g["epoch%d_user_emb" % epoch]) < 1e-5 and rel(pi, g["epoch%d_item_emb" % epoch]) < 1e-5
         rec_list = evaluation.test(rec, ue, ie)  # refquirk mode: the reference's find_k_largest semantics
         got = evaluation.ranking_evaluation(data.test_set, rec_list, [10, 20])
         want = [str(s) for s in g["epoch%d_measures" % epoch]]

@@ -13,7 +13,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 SHAPES = {"c2": (6040, 3706, 750_000), "c3": (30_000, 41_000, 1_000_000), "c4": (52_000, 92_000, 3_000_000),
-          "c5s": (1_250_000, 2_000_000, 125_000_000)}
+          "c5s": (1_250_000, 2_000_000, 125_000_000), "c5e": (1_250_000, 250_000, 125_000_000)}
 
 
 def main():
