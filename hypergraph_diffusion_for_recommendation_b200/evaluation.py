@@ -222,10 +222,13 @@ def ranking_evaluation_ids(truth_indptr, truth_items, rec_ids, N):
     return measure
 
 
-def ranking_evaluation_device(truth_indptr, truth_items, rec_ids: torch.Tensor, N):
-    """``ranking_evaluation_ids`` with the per-user work (set intersections, DCG) on the device (``hgr_rank_metrics``):
-    ``rec_ids`` is the device id matrix of ``fullrank_topk``; only ``[n_test, len(N)]`` hits / DCG values come back.  The
-    sums over users run on the host in the reference's order, so the strings are identical to ``ranking_evaluation``."""
+def ranking_evaluation_device(truth_indptr, truth_items, rec_ids: torch.Tensor, N, host_sums: bool = False):
+    """``ranking_evaluation_ids`` on the device: the per-user work (set intersections, DCG: ``hgr_rank_metrics``) AND the sums
+    over users (``hgr_rank_metric_sums``: one thread per sum adds the users' terms in the reference's order, python's
+    ``sum()`` arithmetic included), so only ``3 x len(N)`` numbers come back and the strings are identical to
+    ``ranking_evaluation``.  ``host_sums=True`` keeps the sums in python loops (the cross-check of the device reducer)."""
+    import sys
+
     dev = rec_ids.device
     rec_ids = rec_ids.to(torch.int32).contiguous()
     n_users, k = rec_ids.shape
@@ -242,28 +245,43 @@ def ranking_evaluation_device(truth_indptr, truth_items, rec_ids: torch.Tensor, 
     disc = torch.tensor([1.0 / math.log(p + 2, 2) for p in range(k)], dtype=torch.float64, device=dev)
     hits = torch.empty((n_users, len(top)), dtype=torch.int32, device=dev)
     dcg = torch.empty((n_users, len(top)), dtype=torch.float64, device=dev)
-    _lib.check(_lib.lib().hgr_rank_metrics(rec_ids.data_ptr(), n_users, k, tp_dev.data_ptr(), ti_sorted.data_ptr(), top_dev.data_ptr(),
-                                           len(top), disc.data_ptr(), hits.data_ptr(), dcg.data_ptr(), _lib.stream_ptr()))
-    hits_h, dcg_h = hits.cpu().numpy(), dcg.cpu().numpy()
-    n_truth_l = n_truth.tolist()
+    lib = _lib.lib()
+    _lib.check(lib.hgr_rank_metrics(rec_ids.data_ptr(), n_users, k, tp_dev.data_ptr(), ti_sorted.data_ptr(), top_dev.data_ptr(),
+                                    len(top), disc.data_ptr(), hits.data_ptr(), dcg.data_ptr(), _lib.stream_ptr()))
     total_num = int(n_truth.sum())
     idcg_tab = [0.0]
     for j in range(max(max(top), k)):
         idcg_tab.append(idcg_tab[-1] + 1.0 / math.log(j + 2, 2))
+    if host_sums:
+        hits_h, dcg_h = hits.cpu().numpy(), dcg.cpu().numpy()
+        n_truth_l = n_truth.tolist()
+    else:
+        idcg_dev = torch.tensor(idcg_tab, dtype=torch.float64, device=dev)
+        hit_sum = torch.empty(len(top), dtype=torch.int64, device=dev)
+        rec_sum = torch.empty(len(top), dtype=torch.float64, device=dev)
+        ndcg_sum = torch.empty(len(top), dtype=torch.float64, device=dev)
+        _lib.check(lib.hgr_rank_metric_sums(hits.data_ptr(), dcg.data_ptr(), tp_dev.data_ptr(), n_users, len(top), top_dev.data_ptr(),
+                                            idcg_dev.data_ptr(), len(idcg_tab), 1 if sys.version_info >= (3, 12) else 0,
+                                            hit_sum.data_ptr(), rec_sum.data_ptr(), ndcg_sum.data_ptr(), _lib.stream_ptr()))
+        hit_sum, rec_sum, ndcg_sum = hit_sum.tolist(), rec_sum.tolist(), ndcg_sum.tolist()
     measure = []
     for n in N:
         q = top.index(int(n))
-        hits_l = hits_h[:, q].tolist()
-        hit_num = 0
-        for x in hits_l:
-            hit_num += x
+        if host_sums:
+            hits_l = hits_h[:, q].tolist()
+            hit_num = 0
+            for x in hits_l:
+                hit_num += x
+            recall_list = [a / b for a, b in zip(hits_l, n_truth_l)]
+            sum_recall = sum(recall_list)
+            sum_ndcg = 0
+            for d, m in zip(dcg_h[:, q].tolist(), n_truth_l):
+                sum_ndcg += d / idcg_tab[min(m, n)]
+        else:
+            hit_num, sum_recall, sum_ndcg = hit_sum[q], rec_sum[q], ndcg_sum[q]
         hr = round(hit_num / total_num, 5)
-        prec = round(sum(hits_l) / (n_users * n), 5)
-        recall_list = [a / b for a, b in zip(hits_l, n_truth_l)]
-        recall = round(sum(recall_list) / len(recall_list), 5)
-        sum_ndcg = 0
-        for d, m in zip(dcg_h[:, q].tolist(), n_truth_l):
-            sum_ndcg += d / idcg_tab[min(m, n)]
+        prec = round(hit_num / (n_users * n), 5)
+        recall = round(sum_recall / n_users, 5)
         ndcg = round(sum_ndcg / n_users, 5)
         measure.append('Top ' + str(n) + '\n')
         measure += ['Hit Ratio:' + str(hr) + '\n', 'Precision:' + str(prec) + '\n', 'Recall:' + str(recall) + '\n',

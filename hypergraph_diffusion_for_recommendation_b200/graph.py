@@ -189,6 +189,33 @@ class DeviceCSR:
     def _nnz(self) -> int:
         return int(self.indices.numel())
 
+    is_sparse = True  # what `adj.is_sparse` answered for the COO tensor this handle replaces
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        """The reference's encoders call ``torch.sparse.mm(self.sparse_norm_adj, x)`` themselves (model/graph/LightGCN.py:133,
+        HCCF.py:199, SGL.py:156-160 ...).  With a ``DeviceCSR`` as the first operand torch hands the call over to this hook, and
+        the product runs on ``hgr_spmm_f32`` with its hand-written backward (``ops.spmm``) -- the unmodified encoder source keeps
+        working.  Anything else torch might do with the handle is refused loudly."""
+        import torch as _t
+
+        name = getattr(func, "__name__", "")
+        if name in ("_sparse_mm", "mm", "matmul", "spmm") and len(args) == 2 and isinstance(args[0], DeviceCSR) and isinstance(args[1], _t.Tensor):
+            from . import ops
+
+            return ops.spmm(args[0], args[1])
+        raise _lib.HgrError("torch.%s is not supported on a DeviceCSR (only adj @ dense: torch.sparse.mm / torch.mm / torch.matmul)" % name)
+
+    def _indices(self) -> torch.Tensor:
+        """COO coordinates ``[2, nnz]`` int64, row-major -- what ``sparse_tensor._indices()`` gave the reference (LightGCN.py:118
+        builds an unused all-ones copy from it).  Returned on the HOST: the legacy ``torch.sparse.FloatTensor(i, v, shape)``
+        constructor those lines use only takes CPU tensors."""
+        rows = torch.repeat_interleave(torch.arange(self.shape[0], device=self.device, dtype=torch.int64), self.indptr[1:] - self.indptr[:-1])
+        return torch.stack([rows, self.indices.to(torch.int64)]).cpu()
+
+    def _values(self) -> torch.Tensor:
+        return self.values.cpu()
+
     def t(self) -> "DeviceCSR":
         if self.symmetric:
             return self

@@ -325,6 +325,18 @@ int hgr_bpr_sample(const int32_t *edge_u, const int32_t *edge_i, int64_t n_edges
 int hgr_rank_metrics(const int32_t *ids, int64_t n_test, int32_t K, const int64_t *truth_indptr, const int32_t *truth_items,
                      const int32_t *top_n, int32_t n_top, const double *disc, int32_t *hits, double *dcg, hgr_stream_t stream);
 
+/* The sums over test users that turn those per-user pieces into the metric values (util/evaluation.py: Metric.hit_ratio :18-30,
+ * precision :45-48, recall :50-53, NDCG :85-97), accumulated on the device in the reference's own order of additions:
+ *   hit_sum[q]    = sum_r hits[r][q]                                  (integers)
+ *   recall_sum[q] = sum_r hits[r][q] / n_truth(r)                     (python's builtin sum(): `compensated` != 0 selects the
+ *                                                                      Neumaier summation of python >= 3.12, 0 the plain one)
+ *   ndcg_sum[q]   = sum_r dcg[r][q] / idcg_tab[min(n_truth(r), N_q)]  (plain sequential `+=`, users in row order)
+ * idcg_tab[k] = sum_{p<k} 1 / math.log(p + 2, 2), accumulated by the host in python doubles (idcg_len entries).
+ * One thread per sum walks the users in order (the order IS the result); the per-user terms are formed in parallel. */
+int hgr_rank_metric_sums(const int32_t *hits, const double *dcg, const int64_t *truth_indptr, int64_t n_test, int32_t n_top,
+                         const int32_t *top_n, const double *idcg_tab, int32_t idcg_len, int32_t compensated, int64_t *hit_sum,
+                         double *recall_sum, double *ndcg_sum, hgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

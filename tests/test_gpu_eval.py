@@ -232,3 +232,74 @@ def test_device_metric_reducer_matches_host_and_oracle_with_duplicates_and_unkno
     assert host[:1] == ["Top 5\n"]
     want = O.ranking_evaluation([list(t) for t in truth], rec, [10, 20, 40])
     assert E.ranking_evaluation_device(ptr, items, cuda(rec.astype(np.int32)), [10, 20, 40]) == want
+
+
+def test_device_metric_sums_reproduce_the_python_sums_bit_for_bit(E):
+    """hgr_rank_metric_sums against the python loops it replaces (host_sums=True), on 200 000 users: the sums are sequential
+    double additions in user order (Neumaier-compensated for the recall list under python >= 3.12), so the UNROUNDED values are
+    equal, not just the 5-decimal strings."""
+    import sys
+
+    import torch
+
+    rng = np.random.default_rng(33)
+    n_users, n_items, k = 200_000, 5000, 20
+    n_truth = rng.integers(1, 40, n_users)
+    ptr = np.zeros(n_users + 1, np.int64)
+    np.cumsum(n_truth, out=ptr[1:])
+    items = rng.integers(0, n_items, int(ptr[-1]))
+    rec = rng.integers(0, n_items, (n_users, k)).astype(np.int32)
+    rec[::3, 1] = items[ptr[:-1][::3]]  # plenty of hits
+    rd = cuda(rec)
+    for top in ([10, 20], [20]):
+        assert E.ranking_evaluation_device(ptr, items, rd, top) == E.ranking_evaluation_device(ptr, items, rd, top, host_sums=True)
+    # the raw sums of one call, device against numpy / python arithmetic
+    import ctypes as C
+    import math
+
+    from hypergraph_diffusion_for_recommendation_b200 import _lib
+
+    hits_ref = np.array([len(set(items[ptr[r]:ptr[r + 1]].tolist()) & set(rec[r].tolist())) for r in range(0, n_users, 997)])
+    lib = _lib.lib()
+    tp = cuda(ptr)
+    order = np.lexsort((items, np.repeat(np.arange(n_users), n_truth)))
+    ti = cuda(items[order].astype(np.int32))
+    top_dev = cuda(np.array([20], np.int32))
+    disc = cuda(np.array([1.0 / math.log(p + 2, 2) for p in range(k)], np.float64))
+    hits = torch.empty((n_users, 1), dtype=torch.int32, device="cuda")
+    dcg = torch.empty((n_users, 1), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hgr_rank_metrics(rd.data_ptr(), n_users, k, tp.data_ptr(), ti.data_ptr(), top_dev.data_ptr(), 1, disc.data_ptr(),
+                                    hits.data_ptr(), dcg.data_ptr(), st))
+    assert np.array_equal(hits[::997, 0].cpu().numpy(), hits_ref)
+    idcg = [0.0]
+    for j in range(20):
+        idcg.append(idcg[-1] + 1.0 / math.log(j + 2, 2))
+    out_h = torch.empty(1, dtype=torch.int64, device="cuda")
+    out_r = torch.empty(1, dtype=torch.float64, device="cuda")
+    out_n = torch.empty(1, dtype=torch.float64, device="cuda")
+    for comp in (0, 1):
+        _lib.check(lib.hgr_rank_metric_sums(hits.data_ptr(), dcg.data_ptr(), tp.data_ptr(), n_users, 1, top_dev.data_ptr(),
+                                            cuda(np.array(idcg)).data_ptr(), len(idcg), comp, out_h.data_ptr(), out_r.data_ptr(),
+                                            out_n.data_ptr(), st))
+        h = hits[:, 0].cpu().numpy().tolist()
+        terms = [a / b for a, b in zip(h, n_truth.tolist())]
+        if comp == 0:
+            want = 0.0
+            for x in terms:
+                want += x
+        else:  # Neumaier, as CPython >= 3.12 sums floats
+            want, c = 0.0, 0.0
+            for x in terms:
+                t = want + x
+                c += (want - t) + x if abs(want) >= abs(x) else (x - t) + want
+                want = t
+            if c and math.isfinite(c):
+                want += c
+            if sys.version_info >= (3, 12):
+                assert want == sum(terms)
+        assert out_r.item() == want and out_h.item() == sum(h)
+        nd = 0
+        for d, m in zip(dcg[:, 0].cpu().numpy().tolist(), n_truth.tolist()):
+            nd += d / idcg[min(m, 20)]
+        assert out_n.item() == nd
