@@ -434,6 +434,10 @@ def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, prima
         per_step = []
         launches0 = _lib.launch_count()
         ops.PROFILE_EVENTS = spmm_events if kind == "device" else None
+        if world > 1 and kind == "device":  # time this rank's waits in the cross-rank barriers and its peer-store copy kernels
+            adj.copy_events = []
+            for pool in adj._pools.values():
+                pool.wait_events = []
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
         if not small:
@@ -489,6 +493,12 @@ def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, prima
                 phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1) / steps
         exchange["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
         adj.phase_events = None
+        waits = [e for pool in adj._pools.values() for e in (pool.wait_events or [])]
+        exchange["barriers_per_step"] = len(waits) / steps
+        exchange["barrier_wait_ms_per_step_rank0"] = round(sum(a.elapsed_time(b) for a, b in waits) / steps, 3)
+        exchange["copy_kernel_ms_per_step_rank0"] = round(sum(a.elapsed_time(b) for a, b in adj.copy_events) / steps, 3)
+        for pool in adj._pools.values():
+            pool.wait_events = None
     e2e_ms, _, _ = timed("e2e")
     eval_info = run_eval(job, model, eval_inputs, part, adj, workload) if eval_inputs is not None else None
     if facade is not None and not primary:

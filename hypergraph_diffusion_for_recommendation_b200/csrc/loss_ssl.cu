@@ -292,7 +292,9 @@ __global__ void __launch_bounds__(256) ssl_scatter_kernel(const float *__restric
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int d = lane + 32 * q;
-        if (d < D) dE[r * D + d] = normalize ? (g[q] - y[q] * gy) / n : g[q];
+        // dE is zero-filled by the caller; with unique ids (every reference caller passes torch.unique) one add per element is
+        // a store, and a caller that repeats an id gets the SUM of its gradients, like index_select's backward, instead of the last one
+        if (d < D) atomicAdd(dE + r * D + d, normalize ? (g[q] - y[q] * gy) / n : g[q]);
     }
 }
 

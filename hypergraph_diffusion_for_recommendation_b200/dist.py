@@ -62,18 +62,25 @@ class Partition:
         return torch.div(i, self.ip, rounding_mode="floor") * self.n_loc + self.up + i % self.ip
 
 
-def local_block(part: Partition, rank: int, u: torch.Tensor, i: torch.Tensor):
-    """``A[own rows, :]`` of the normalised bipartite adjacency of the UNIQUE pairs ``(u, i)``, as
-    ``(indptr int64 [n_loc + 1], indices int32, values float32)`` with permuted column ids stored in original
-    ascending-id order.  Values are ``d[row] * d[col]`` with ``d = np.power(deg, -0.5)`` (one fp32 multiply, the value
-    scipy's ``D A D`` product leaves for unit weights): bit-identical to ``Interaction.norm_adj``."""
+def local_block(part: Partition, rank: int, u: torch.Tensor, i: torch.Tensor, use_builder: bool | None = None):
+    """``A[own rows, :]`` of the normalised bipartite adjacency of the interaction list ``(u, i)``, as
+    ``(indptr int64 [n_loc + 1], indices int32, values float32)`` with permuted column ids.  The permutation is monotonic inside
+    the user range and inside the item range, so ascending permuted ids ARE the original ascending order of a row: every output
+    row is accumulated in the single-GPU order.  Values are ``(d[row] * m) * d[col]`` with ``d = np.power(deg, -0.5)`` from the
+    host's table and ``m`` the multiplicity of a repeated pair: bit-identical to ``Interaction.norm_adj``.
+
+    On CUDA the block comes out of the product builder (csrc/graph_build.cu: radix sort of THIS RANK's entries only -- the
+    interactions whose user or item it owns -- duplicates summed, LUT degree scale); the torch sort / bincount form below is the
+    host-logic path of the gloo CPU tests."""
     dev = u.device
+    if use_builder is None:
+        use_builder = dev.type == "cuda"
     u = u.to(torch.int64)
     i = i.to(torch.int64)
+    # degrees count every listed interaction (duplicates included), like the row sums the reference normalises by; in a job
+    # whose ranks hold disjoint slices of the list this is the one all_reduce of the build
     deg_u = torch.bincount(u, minlength=part.n_users)
     deg_i = torch.bincount(i, minlength=part.n_items)
-    # deg^-1/2 through the host's np.power table, like graph.build_norm_adj: numpy's float32 pow is what the
-    # reference's values are made of and it is not correctly rounded (SURVEY.md F10)
     from .graph import host_pow_lut
 
     max_deg = int(max(deg_u.max().item() if deg_u.numel() else 0, deg_i.max().item() if deg_i.numel() else 0))
@@ -81,7 +88,25 @@ def local_block(part: Partition, rank: int, u: torch.Tensor, i: torch.Tensor):
     du, di = lut[deg_u], lut[deg_i]
     u0, u1 = part.users_of(rank)
     i0, i1 = part.items_of(rank)
-    # user rows: columns are items, ascending item id
+    if use_builder:
+        from . import graph
+
+        mu = (u >= u0) & (u < u1)
+        mi = (i >= i0) & (i < i1)
+        rows = torch.cat([u[mu] - u0, part.up + (i[mi] - i0)]).to(torch.int32)
+        cols = torch.cat([part.perm_item(i[mu]), part.perm_user(u[mi])]).to(torch.int32)
+        del mu, mi
+        indptr, indices, values, _ = graph._build("coo", rows, cols, part.n_loc, part.n_glob)
+        del rows, cols
+        d_rows = torch.zeros(part.n_loc, dtype=torch.float32, device=dev)
+        d_rows[:u1 - u0] = du[u0:u1]
+        d_rows[part.up:part.up + (i1 - i0)] = di[i0:i1]
+        d_cols = torch.zeros(part.n_glob, dtype=torch.float32, device=dev)
+        d_cols[part.perm_user(torch.arange(part.n_users, device=dev))] = du
+        d_cols[part.perm_item(torch.arange(part.n_items, device=dev))] = di
+        graph._scale(indptr, indices, values, part.n_loc, d_rows, d_cols)
+        return indptr, indices, values
+    # host-logic path (unique pairs): user rows: columns are items, ascending item id
     m = (u >= u0) & (u < u1)
     key = torch.sort((u[m] - u0) * part.n_items + i[m]).values
     ru, ci = torch.div(key, part.n_items, rounding_mode="floor"), key % part.n_items
@@ -147,6 +172,7 @@ class SymmetricPool:
             self.hdls.append(h)
             self.ptrs.append([int(p) for p in h.buffer_ptrs])
         self.next = 0
+        self.wait_events = None
 
     def take(self) -> int:
         k = self.next
@@ -154,7 +180,15 @@ class SymmetricPool:
         return k
 
     def barrier(self, k: int) -> None:
-        self.hdls[k].barrier(channel=0)
+        ev = self.wait_events
+        if ev is not None:  # bench: how long this rank sits in the cross-rank barriers of a step
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.hdls[k].barrier(channel=0)
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            self.hdls[k].barrier(channel=0)
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -210,6 +244,7 @@ class DistGraph:
         self._published = {}  # pool slot -> (tensor kept alive, version): local rows whose gathered copy sits in that slot
         self.publish_copy = os.environ.get("HGR_PUBLISH_COPY", "1") != "0"
         self.n_fused, self.n_collective, self.n_published = 0, 0, 0
+        self.copy_events = []
 
     def _nnz(self):
         return self._nnz_local
@@ -269,7 +304,14 @@ class DistGraph:
         pool = self.pool(x.shape[1])
         k = pool.take()
         self._published.pop(k, None)
-        self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc)
+        if pool.wait_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc)
+            e1.record()
+            self.copy_events.append((e0, e1))
+        else:
+            self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc)
         pool.barrier(k)
         self._published[k] = (x, x._version)
         self.n_published += 1
@@ -281,7 +323,8 @@ class DistGraph:
         if self.fused:
             pool = self._pools.get(x.shape[1])
             for k, (t, ver) in self._published.items():
-                if t is x or (t.data_ptr() == x.data_ptr() and t.shape == x.shape and t._version == ver == x._version):
+                # same storage AND unmodified since it was published (an optimizer step on a parameter bumps _version)
+                if t.data_ptr() == x.data_ptr() and t.shape == x.shape and t._version == ver == x._version:
                     return pool.bufs[k]
             if self.publish_copy and x.dim() == 2 and x.shape[0] == self.part.n_loc and x.dtype == torch.float32 \
                     and x.shape[1] % 4 == 0 and self.pool(x.shape[1]) is not None:

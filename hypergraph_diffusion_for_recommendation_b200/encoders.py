@@ -93,8 +93,8 @@ class LGCN_Encoder(nn.Module):
 
 class SGL_Encoder(nn.Module):
     """``SGL_Encoder`` (model/graph/SGL.py:110-180): LightGCN propagation on the clean graph or on a perturbed one (a single
-    ``DeviceCSR`` or one per layer), two augmented views per batch and ``InfoNCE`` between them.  ``data`` must expose the
-    dense-id interaction list as ``data.train_u / data.train_i`` (device int tensors) for ``graph_reconstruction``."""
+    ``DeviceCSR`` or one per layer), two augmented views per batch and ``InfoNCE`` between them.  ``graph_reconstruction`` reads the
+    interaction list from ``data.dense_training_pairs()`` (the ``data.Interaction`` facade) or ``data.train_u / data.train_i``."""
 
     def __init__(self, data, emb_size, drop_rate, n_layers, temp, aug_type):
         super(SGL_Encoder, self).__init__()
@@ -116,11 +116,23 @@ class SGL_Encoder(nn.Module):
         # the reference's condition `self.aug_type==0 or 1` is always true: one perturbed graph for all layers
         return self.random_graph_augment()
 
+    def _training_pairs(self):
+        """Distinct dense (user, item) pairs on the device: the reference drops nodes / edges of ``interaction_mat.nonzero()``
+        (data/augmentor.py:12-42), i.e. of DISTINCT interactions with unit weights, whatever the file repeats."""
+        pairs = getattr(self, "_pairs", None)
+        if pairs is None:
+            d = self.data
+            u, i = d.dense_training_pairs() if hasattr(d, "dense_training_pairs") else (d.train_u, d.train_i)
+            dev = self.embedding_dict['user_emb'].device
+            key = torch.unique(torch.as_tensor(u).to(dev, torch.int64) * d.n_items + torch.as_tensor(i).to(dev, torch.int64))
+            pairs = self._pairs = (torch.div(key, d.n_items, rounding_mode="floor").to(torch.int32), (key % d.n_items).to(torch.int32))
+        return pairs
+
     def random_graph_augment(self):
         from . import augmentor
 
-        return augmentor.random_graph_augment(self.data.train_u, self.data.train_i, self.data.n_users, self.data.n_items,
-                                              self.aug_type, self.drop_rate)
+        u, i = self._training_pairs()
+        return augmentor.random_graph_augment(u, i, self.data.n_users, self.data.n_items, self.aug_type, self.drop_rate)
 
     def forward(self, perturbed_adj=None):
         ego_embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
@@ -312,10 +324,12 @@ class EquivSetConvScatter(nn.Module):
         return self._inc
 
     def forward(self, X, vertex, edges, X0):
-        inc = self.incidence(vertex, edges, X.shape[-2])
-        Xe = ops.segment_mean_to_edges(inc, self.W1(X))
-        Xv = ops.segment_mean_to_nodes(inc, Xe)
-        X = (1 - self.alpha) * Xv + self.alpha * X0
+        return self.forward_inc(X, self.incidence(vertex, edges, X.shape[-2]), X0)
+
+    def forward_inc(self, X, inc, X0):
+        """The same convolution on an incidence pair the caller built once (``graph.Incidence``)."""
+        Xv = ops.segment_mean_to_nodes(inc, ops.segment_mean_to_edges(inc, self.W1(X)))
+        X = Xv if self.alpha == 0 else (1 - self.alpha) * Xv + self.alpha * X0
         return self.W(X)
 
 

@@ -439,6 +439,73 @@ class Incidence:
         self.n_edges, self.n_nodes = to_edges.shape
 
 
+def _csr_keys(m: DeviceCSR) -> torch.Tensor:
+    rows = torch.repeat_interleave(torch.arange(m.shape[0], device=m.device, dtype=torch.int64), m.indptr[1:] - m.indptr[:-1])
+    return rows * m.shape[1] + m.indices.to(torch.int64)
+
+
+def pair_positions(inc: Incidence, vertex, edges):
+    """Where each (vertex, hyperedge) pair sits in ``inc.to_edges`` and in ``inc.to_nodes`` (both canonical CSR): the maps that
+    let a per-pair weight vector (HD2's attention, model/graph/HD2.py:630-632) become CSR values.  Pairs must be unique."""
+    dev = inc.to_edges.device
+    v = torch.as_tensor(vertex).to(dev, torch.int64)
+    e = torch.as_tensor(edges).to(dev, torch.int64)
+    pos_e = torch.searchsorted(_csr_keys(inc.to_edges), e * inc.n_nodes + v)
+    pos_n = torch.searchsorted(_csr_keys(inc.to_nodes), v * inc.n_edges + e)
+    return pos_e, pos_n
+
+
+def incidence_from_csr(h: DeviceCSR) -> Incidence:
+    """The star expansion HGNN_HD4 feeds to EquivSetGNN2 (model/graph/HGNN_HD4.py:389,397; EquivSetGNN2.py:105-133):
+    ``(V, E) = nonzero(dense(H) > 0)`` of a matrix that is already sparse on the device -- every stored entry once, whatever
+    its multiplicity.  No dense (U+I)^2 copy, no ``nonzero`` per forward."""
+    rows = torch.repeat_interleave(torch.arange(h.shape[0], device=h.device, dtype=torch.int32), h.indptr[1:] - h.indptr[:-1])
+    keep = h.values > 0
+    return build_incidence(rows[keep], h.indices[keep], h.shape[0], h.shape[1], device=h.device)
+
+
+class HyperNormAdj:
+    """``Graph.normalize_graph_mat_hyper`` (data/graph.py:28-42): ``Dv^-1/2 H De^-1 H^T Dv^-1/2`` kept FACTORED,
+    ``left = (Dv^-1/2 H) De^-1`` ([n_v, n_e]) and ``right = H^T Dv^-1/2`` ([n_e, n_v]), both ``DeviceCSR`` with scipy's
+    roundings.  The reference multiplies the factors out with scipy (a two-hop matrix: nearly dense for a power-law graph);
+    here the operator is applied as two propagations, which is also how every encoder uses it."""
+
+    def __init__(self, left: DeviceCSR, right: DeviceCSR):
+        self.left, self.right = left, right
+        self.shape = (left.shape[0], right.shape[1])
+        self.device = left.device
+
+    def matmul(self, x: torch.Tensor) -> torch.Tensor:
+        from . import ops
+
+        return ops.spmm(self.left, ops.spmm(self.right, x))
+
+    __matmul__ = matmul
+
+    def t(self):
+        return self  # symmetric operator
+
+
+def normalize_graph_mat_hyper(h: DeviceCSR) -> HyperNormAdj:
+    dev = h.device
+    n_v, n_e = h.shape
+    rows = torch.repeat_interleave(torch.arange(n_v, device=dev), h.indptr[1:] - h.indptr[:-1])
+    rowsum = torch.zeros(n_v, dtype=torch.float32, device=dev).index_add_(0, rows, h.values)
+    colsum = torch.zeros(n_e, dtype=torch.float32, device=dev).index_add_(0, h.indices.long(), h.values)
+    rs, cs = rowsum.to(torch.int32), colsum.to(torch.int32)
+    if not (torch.equal(rs.float(), rowsum) and torch.equal(cs.float(), colsum)):
+        raise _lib.HgrError("normalize_graph_mat_hyper on the device needs integer row / column sums (unit-weight incidences)")
+    dv, de = _degree_scale(rs, -0.5), _degree_scale(cs, -1.0)
+    lv = h.values.clone()
+    _scale(h.indptr, h.indices, lv, n_v, dv, de)  # (dv[r] * h) * de[c]: scipy's d_v.dot(adj).dot(d_e)
+    left = DeviceCSR(h.indptr, h.indices, lv, h.shape, chunk_nnz=h.chunk_nnz)
+    ht = h.t()
+    rv = ht.values.clone()
+    _scale(ht.indptr, ht.indices, rv, n_e, None, dv)  # h * dv[c]: adj.T.dot(d_v)
+    right = DeviceCSR(ht.indptr, ht.indices, rv, ht.shape, chunk_nnz=ht.chunk_nnz)
+    return HyperNormAdj(left, right)
+
+
 def build_incidence(vertex, edges, n_nodes: int, n_edges: int | None = None, device="cuda") -> Incidence:
     dev = torch.device(device)
     v, e = _as_i32(vertex, dev), _as_i32(edges, dev)

@@ -14,6 +14,12 @@ import torch
 from . import _lib
 
 
+def _raise_on_bad_index(bad: torch.Tensor, what: str) -> None:
+    """The kernels skip ids outside the tables and count them; the reference's ``emb[idx]`` raises IndexError.  Surface the
+    counter without a host synchronisation: a device-side assertion (fatal, like the reference's exception; capturable)."""
+    torch._assert_async(bad[0] == 0, "libhgr: %s got indices outside the embedding tables (see include/hgr.h)" % what)
+
+
 def _idx(t: torch.Tensor, device) -> torch.Tensor:
     # the reference's sampler yields CPU LongTensors (util/sampler.py:261-263): one H2D copy here
     return t.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
@@ -40,8 +46,9 @@ class _BprL2(torch.autograd.Function):
                                           user_tab.shape[1], u.data_ptr(), p.data_ptr(), n.data_ptr(), batch, float(reg),
                                           float(batch_size), out.data_ptr(), saved.data_ptr(), saved.numel(), bad.data_ptr(),
                                           _lib.stream_ptr()))
+        _raise_on_bad_index(bad, "bpr_l2_from_tables")
         ctx.save_for_backward(user_tab, item_tab, u, p, n, saved)
-        ctx.reg, ctx.batch_size, ctx.bad = float(reg), float(batch_size), bad
+        ctx.reg, ctx.batch_size = float(reg), float(batch_size)
         return out
 
     @staticmethod
@@ -74,6 +81,7 @@ class _BprL2Sharded(torch.autograd.Function):
         _lib.check(lib.hgr_bpr_l2_fwd_f32(full.data_ptr(), full.data_ptr(), full.shape[0], full.shape[0], full.shape[1], u.data_ptr(),
                                           p.data_ptr(), n.data_ptr(), batch, float(reg), float(batch_size), out.data_ptr(),
                                           saved.data_ptr(), saved.numel(), bad.data_ptr(), _lib.stream_ptr()))
+        _raise_on_bad_index(bad, "bpr_l2_sharded (ids must index the gathered table: Partition.perm_user / perm_item)")
         ctx.save_for_backward(full, u, p, n, saved)
         ctx.meta = (int(row_lo), int(own.shape[0]), float(reg), float(batch_size))
         return out
@@ -146,7 +154,7 @@ class _SslLoss(torch.autograd.Function):
                                             _lib.stream_ptr()))
         ctx.save_for_backward(saved, nodes if nodes is not None else torch.empty(0, device=dev))
         ctx.meta = (e1.shape, e2.shape, d, m, float(temp), int(normalize), off, nbytes, nodes is not None)
-        ctx.bad = bad
+        _raise_on_bad_index(bad, "contrastLoss / InfoNCE (a NEGATIVE id is an inactive slot of contrastLoss_padded, an id >= rows is an error)")
         return loss[0]
 
     @staticmethod

@@ -263,6 +263,78 @@ def scatter_mean_conv(inc, x: torch.Tensor) -> torch.Tensor:
     return spmm(inc.to_nodes, spmm(inc.to_edges, x))
 
 
+class _WeightedToEdges(torch.autograd.Function):
+    """``Xe = segment_mean_E(X[V] * att)`` (model/graph/HD2.py:629-633): the node -> hyperedge propagation with one attention weight
+    per (vertex, hyperedge) pair folded into the CSR values (``att / |e|``).  Backward: ``dX`` through the transposed matrix with
+    the same values; ``d att`` is a sampled dense-dense product ``<dXe[e], X[v]> / |e|`` over the pairs (torch gathers)."""
+
+    @staticmethod
+    def forward(ctx, x, att, inc, vertex, edges, pos_e, pos_n):
+        te, tn = inc.to_edges, inc.to_nodes
+        a = att.reshape(-1).to(torch.float32)
+        inv_e = te.values[pos_e]  # 1 / |e| of every pair (the row-normalised incidence)
+        vals = torch.zeros_like(te.values)
+        vals[pos_e] = inv_e * a
+        t_vals = torch.zeros_like(tn.values)
+        t_vals[pos_n] = inv_e * a
+        ctx.w = te.with_values(vals)
+        # the transposed weighted matrix lives on to_nodes' pattern ([n_nodes, n_edges], canonical)
+        ctx.wt = tn.with_values(t_vals)
+        ctx.save_for_backward(x, inv_e, vertex, edges)
+        ctx.att_shape = att.shape
+        return spmm_raw(ctx.w, x)
+
+    @staticmethod
+    def backward(ctx, dxe):
+        x, inv_e, vertex, edges = ctx.saved_tensors
+        dxe = dxe.contiguous()
+        dx = spmm_raw(ctx.wt, dxe) if ctx.needs_input_grad[0] else None
+        datt = None
+        if ctx.needs_input_grad[1]:
+            datt = ((dxe[edges] * x[vertex]).sum(-1) * inv_e).reshape(ctx.att_shape)
+        return dx, datt, None, None, None, None, None
+
+
+def scatter_mean_conv_weighted(inc, x: torch.Tensor, att: torch.Tensor, vertex: torch.Tensor, edges: torch.Tensor, positions=None):
+    """``scatter_mean_conv`` with a per-pair attention weight on the node -> hyperedge stage (HD2's ``EquivSetConv.forward``,
+    model/graph/HD2.py:624-643).  ``positions`` = ``graph.pair_positions(inc, vertex, edges)`` when the caller has them cached."""
+    from .graph import pair_positions
+
+    pos_e, pos_n = positions if positions is not None else pair_positions(inc, vertex, edges)
+    xe = _WeightedToEdges.apply(x, att, inc, vertex.to(x.device).long(), edges.to(x.device).long(), pos_e, pos_n)
+    return spmm(inc.to_nodes, xe)
+
+
+class _PatternMeanConv(torch.autograd.Function):
+    """Scatter-mean message passing through a DENSE 0/1 incidence ``b [n, K]`` (HCCF_diffusion: the sign pattern of the learned
+    ``E W``, model/graph/HCCF_diffusion.py:291-308,382-402): ``Xe = diag(1 / max(|e|, 1)) b^T X``, ``Xv = diag(1 / max(|v|, 1)) b Xe`` on
+    the tall-and-skinny kernels (csrc/hyperedge.cu) instead of ``nonzero`` + two ``torch_scatter`` calls over ~n K / 2 pairs.
+    ``b`` carries no gradient (the reference's ``nonzero(H > 0)`` cuts it)."""
+
+    @staticmethod
+    def forward(ctx, x, b):
+        b = b.contiguous()
+        inv_e = 1.0 / b.sum(0).clamp(min=1.0)
+        inv_v = 1.0 / b.sum(1).clamp(min=1.0)
+        xe = tall_skinny_tn(b, x.contiguous()) * inv_e[:, None]
+        ctx.save_for_backward(b, inv_e, inv_v)
+        return rows_times_small(b, None, xe.contiguous()) * inv_v[:, None]
+
+    @staticmethod
+    def backward(ctx, dy):
+        b, inv_e, inv_v = ctx.saved_tensors
+        g = (dy * inv_v[:, None]).contiguous()
+        dxe = tall_skinny_tn(b, g) * inv_e[:, None]
+        return rows_times_small(b, None, dxe.contiguous()), None
+
+
+def pattern_mean_conv(b: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """See ``_PatternMeanConv``; ``b`` float32 ``[n, K]`` of zeros and ones with K in {32, 64, 128, 256}, ``x`` ``[n, 32|64|128]``."""
+    if not hyperedge_supported(b, x):
+        raise ValueError("pattern_mean_conv: need float32 CUDA b [n, 32|64|128|256] and x [n, 32|64|128], got %s and %s" % (tuple(b.shape), tuple(x.shape)))
+    return _PatternMeanConv.apply(x, b)
+
+
 def segment_mean_to_edges(inc, x: torch.Tensor) -> torch.Tensor:
     """``torch_scatter.scatter(X[V], E, dim=-2, reduce='mean')``"""
     return spmm(inc.to_edges, x)

@@ -330,6 +330,98 @@ def scatter_mean_conv(v, e, x, n_nodes):
 
 # --------------------------------------------------------------------------------------------
 # (a-8, a-9) losses with analytic gradients            util/loss_torch.py:5-9,17-21,32-40,103-110
+def scatter_mean_conv_weighted(v, e, x, att, n_nodes):
+    """The attention-weighted scatter convolution (model/graph/HD2.py:624-643 with W1 = identity, W2 = slice, alpha = 0,
+    before W): ``Xe = segment_mean_E(X[V] * att)``, ``Xv = segment_mean_V(Xe[E])``; ``att`` is one weight per (v, e) pair."""
+    d = x.shape[1]
+    n_e = int(e.max()) + 1
+    xe = np.zeros((n_e, d), dtype=np.float64)
+    np.add.at(xe, e, (x[v] * np.asarray(att, dtype=np.float32).reshape(-1, 1)).astype(np.float64))
+    xe = (xe / np.maximum(np.bincount(e, minlength=n_e), 1)[:, None]).astype(np.float32)
+    xv = np.zeros((n_nodes, d), dtype=np.float64)
+    np.add.at(xv, v, xe[e].astype(np.float64))
+    return (xv / np.maximum(np.bincount(v, minlength=n_nodes), 1)[:, None]).astype(np.float32)
+
+
+def _mlp_w(x, params, prefix):
+    """``MLP`` with one layer and InputNorm (model/layers/MLP.py:109-117): ``Linear(LayerNorm(x))``."""
+    h = layer_norm(x, params[prefix + "normalizations.0.weight"], params[prefix + "normalizations.0.bias"])
+    return (h.astype(np.float64) @ params[prefix + "lins.0.weight"].astype(np.float64).T + params[prefix + "lins.0.bias"]).astype(np.float32)
+
+
+def equiv_set_gnn_scatter(v, e, x, params, prefix, n_nodes):
+    """``EquivSetGNN.forward`` of the scatter form in eval mode (model/layers/layers2/EquivSetGNN2.py:83-103 =
+    model/graph/HCCF_diffusion.py:358-380): ``relu(lin_in(x))`` -> scatter convolution -> ``W`` -> ``relu``."""
+    h = np.maximum((x.astype(np.float64) @ params[prefix + "lin_in.weight"].astype(np.float64).T + params[prefix + "lin_in.bias"]).astype(np.float32), 0)
+    return np.maximum(_mlp_w(scatter_mean_conv(v, e, h, n_nodes), params, prefix + "conv.W."), 0)
+
+
+def hd4_local_aware_encoder(csr, ui_pattern, ego, params, n_layers, n_users):
+    """``LocalAwareEncoder.forward`` of HGNN_HD4 (model/graph/HGNN_HD4.py:391-405), eval mode: every layer but the last is the
+    scatter-form ``EquivSetGNN2`` over ``(V, E) = nonzero(ui_adj > 0)`` (EquivSetGNN2.py:105-133) plus the residual; the last is
+    ``lns[0](HGCNConv(norm_adj, act=False)) + res``.  ``ui_pattern`` = (indptr, indices) of the bipartite adjacency."""
+    ip, ix = ui_pattern
+    v = np.repeat(np.arange(ip.size - 1), np.diff(ip))
+    e = np.asarray(ix)
+    res = ego
+    for k in range(n_layers):
+        if k != n_layers - 1:
+            ego = equiv_set_gnn_scatter(v, e, ego, params, "edhnn_layers.%d." % k, ego.shape[0]) + res
+        else:
+            ego = layer_norm(hgconv(csr, ego, None), params["lns.0.weight"], params["lns.0.bias"]) + res
+    return ego[:n_users], ego[n_users:]
+
+
+def hccf_diffusion_forward(csr, params, n_layers, n_users):
+    """``HCCFEncoder.forward`` of HCCF_diffusion (model/graph/HCCF_diffusion.py:197-217) with keep_rate = 1 and dropout off:
+    per layer ``gcn = A h``; the hypergraph branch is the scatter-form EquivSetGNN over the SIGN pattern of the learned incidence
+    ``H = E0 W`` (``generate_V_E``: ``nonzero(H > 0)``, :382-402), users and items separately, one shared ``edhnnlayer``."""
+    ue, ie = params["embedding_dict.user_emb"], params["embedding_dict.item_emb"]
+    hidden = [np.concatenate([ue, ie], 0)]
+    pats = []
+    for emb, w in ((ue, params["embedding_dict.user_w"]), (ie, params["embedding_dict.item_w"])):
+        h = (emb.astype(np.float64) @ w.astype(np.float64)).astype(np.float32)
+        nz = np.argwhere(h > 0)
+        pats.append((nz[:, 0], nz[:, 1]))
+    gcn_h, hyp_h = [], []
+    for _ in range(n_layers):
+        cur = hidden[-1]
+        gcn = spmm(*csr, cur)
+        hu = equiv_set_gnn_scatter(pats[0][0], pats[0][1], cur[:n_users], params, "edhnnlayer.", n_users)
+        hi = equiv_set_gnn_scatter(pats[1][0], pats[1][1], cur[n_users:], params, "edhnnlayer.", cur.shape[0] - n_users)
+        gcn_h.append(gcn)
+        hyp_h.append(np.concatenate([hu, hi], 0))
+        hidden.append(gcn + hyp_h[-1])
+    emb = hidden[0].copy()
+    for h in hidden[1:]:
+        emb = emb + h
+    return emb[:n_users], emb[n_users:], gcn_h, hyp_h
+
+
+def normalize_graph_mat_hyper(indptr, indices, data, n_cols):
+    """``Graph.normalize_graph_mat_hyper`` (data/graph.py:28-42) in FACTORED form: ``left = (Dv^-1/2 H) De^-1`` and
+    ``right = H^T Dv^-1/2`` as CSR triples, each value with scipy's roundings; the reference's matrix is
+    ``(left @ H^T) @ Dv^-1/2 = left @ right``."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    data = np.asarray(data, dtype=np.float32)
+    n_rows = indptr.size - 1
+    rows = np.repeat(np.arange(n_rows), np.diff(indptr))
+    rowsum = np.zeros(n_rows, dtype=np.float32)
+    np.add.at(rowsum, rows, data)
+    colsum = np.zeros(n_cols, dtype=np.float32)
+    np.add.at(colsum, indices, data)
+    with np.errstate(divide="ignore"):
+        de = np.power(colsum, np.float32(-1))
+        dv = np.power(rowsum, np.float32(-0.5))
+    de[np.isinf(de)] = 0
+    dv[np.isinf(dv)] = 0
+    left = ((dv[rows] * data).astype(np.float32) * de[indices]).astype(np.float32)
+    t_ptr, t_idx, t_val = csr_transpose(indptr, indices, data, n_cols)
+    right = (t_val * dv[t_idx]).astype(np.float32)
+    return (indptr, indices, left), (t_ptr, t_idx, right)
+
+
 # --------------------------------------------------------------------------------------------
 def _sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))

@@ -452,3 +452,28 @@ def test_dhcf_encoder_rectangular_hgconv_matches_reference(hgr, more_golden):
     ((ue * cuda(g["dhcf_wu"])).sum() + (ie * cuda(g["dhcf_wi"])).sum()).backward()
     assert rel_err(m.embedding_dict["user_emb"].grad, g["dhcf_grad_user"]) < 2e-5
     assert rel_err(m.embedding_dict["item_emb"].grad, g["dhcf_grad_item"]) < 2e-5
+
+
+def test_sgl_encoder_on_the_data_facade_with_repeated_training_pairs(hgr):
+    """``SGL_Encoder.graph_reconstruction`` on ``data.Interaction`` (no ``train_u`` attribute there), with a training file
+    that lists some pairs twice: the reference perturbs ``interaction_mat.nonzero()`` -- distinct pairs, unit weights
+    (data/augmentor.py:32-42) -- so the perturbed Laplacian has no weight-2 edge and the edge count is of the distinct pairs."""
+    from hypergraph_diffusion_for_recommendation_b200 import data as D
+
+    rng = np.random.default_rng(4)
+    pairs = np.unique(np.stack([rng.integers(0, 40, 600), 1000 + rng.integers(0, 70, 600)], 1), axis=0)
+    listed = np.concatenate([pairs, pairs[::5]])  # every fifth pair twice
+    train = [[int(u), int(i), 1.0] for u, i in listed]
+    test = [[int(u), int(i), 1.0] for u, i in pairs[::7]]
+    data = D.Interaction(None, train, test)
+    enc = hgr.enc.SGL_Encoder(data, 64, 0.25, 2, 0.2, 1).cuda()
+    adj = enc.graph_reconstruction()
+    ip, ix, dv = adj.to_host(drop_zeros=True)
+    kept = int(pairs.shape[0] * 0.75)
+    assert ix.size == 2 * kept                                   # int(E_distinct * (1 - drop_rate)) edges, both directions
+    deg = np.diff(ip).astype(np.float64)
+    rows = np.repeat(np.arange(ip.size - 1), np.diff(ip))
+    want = 1.0 / np.sqrt(deg[rows] * deg[ix])                     # unit weights: every value is d[r] d[c]
+    assert np.abs(dv - want).max() < 1e-6
+    ue, ie = enc(adj)
+    assert ue.shape == (data.n_users, 64) and torch.isfinite(ue).all() and torch.isfinite(ie).all()

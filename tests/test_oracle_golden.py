@@ -250,3 +250,68 @@ def test_sht_and_dhcf_encoders_against_the_reference():
                             float(g["dhcf_args"][2]))
     # the reference multiplies a DENSIFIED matrix (dense fp32 GEMM order); same sums, other order
     assert rel(ue, g["dhcf_user_out"]) < 1e-5 and rel(ie, g["dhcf_item_out"]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ scatter-form consumers (SURVEY a-6)
+@pytest.fixture(scope="module")
+def scat():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scatter_encoders.npz"))
+
+
+def _scat_graph(scat):
+    from hypergraph_diffusion_for_recommendation_b200.synth import reference_dense_ids
+
+    du, di, id2u, id2i = reference_dense_ids(scat["train"][:, 0].astype(np.int64), scat["train"][:, 1].astype(np.int64))
+    return du, di, id2u.size, id2i.size
+
+
+def _params(npz, prefix):
+    return {k[len(prefix):]: npz[k] for k in npz.files if k.startswith(prefix)}
+
+
+def test_oracle_hd4_local_aware_encoder_matches_the_reference(scat):
+    """HGNN_HD4.LocalAwareEncoder (model/graph/HGNN_HD4.py:391-405) as run by tests/golden/make_golden_scatter_encoders.py."""
+    du, di, nu, ni = _scat_graph(scat)
+    csr = O.build_norm_adj(du, di, nu, ni)
+    ip, ix, _ = O.bipartite_adjacency(du, di, nu, ni)
+    ue, ie = O.hd4_local_aware_encoder(csr, (ip, ix), scat["hd4_E0"], _params(scat, "hd4_param/"), 2, nu)
+    assert rel_err(ue, scat["hd4_user_out"]) < RTOL and rel_err(ie, scat["hd4_item_out"]) < RTOL
+
+
+def test_oracle_hccf_diffusion_encoder_matches_the_reference(scat):
+    """HCCF_diffusion.HCCFEncoder (model/graph/HCCF_diffusion.py:197-217) with keep_rate 1, eval mode."""
+    du, di, nu, ni = _scat_graph(scat)
+    csr = O.build_norm_adj(du, di, nu, ni)
+    hu, hi, gcn_h, hyp_h = O.hccf_diffusion_forward(csr, _params(scat, "hdf_param/"), 2, nu)
+    assert rel_err(hu, scat["hdf_user_out"]) < RTOL and rel_err(hi, scat["hdf_item_out"]) < RTOL
+    for l in range(2):
+        assert rel_err(gcn_h[l], scat["hdf_gcn_%d" % l]) < RTOL and rel_err(hyp_h[l], scat["hdf_hyp_%d" % l]) < RTOL
+
+
+def test_oracle_attention_weighted_scatter_matches_the_reference(scat):
+    """HD2.EquivSetConv.forward (model/graph/HD2.py:624-643): per-edge attention on the node -> hyperedge stage."""
+    xv = O.scatter_mean_conv_weighted(scat["att_V"], scat["att_E"], scat["att_X"], scat["att_atts"], scat["att_X"].shape[0])
+    y = O._mlp_w(xv, _params(scat, "att_param/"), "W.")
+    assert rel_err(y, scat["att_Y"]) < RTOL
+
+
+def test_oracle_normalize_graph_mat_hyper_matches_the_reference(scat):
+    """Graph.normalize_graph_mat_hyper (data/graph.py:28-42): the factored form reproduces the reference's matrix -- its values
+    after multiplying the two factors out (float64 product of fp32 factors, 1e-6) and its action on a table."""
+    import scipy.sparse as sp
+
+    du, di, nu, ni = _scat_graph(scat)
+    for name, (ip, ix, dv), shape in (("inter", O.interaction_matrix(du, di, nu, ni), (nu, ni)),
+                                      ("adj", O.bipartite_adjacency(du, di, nu, ni), (nu + ni, nu + ni))):
+        (lp, li, lv), (rp, ri, rv) = O.normalize_graph_mat_hyper(ip, ix, dv, shape[1])
+        left = sp.csr_matrix((lv.astype(np.float64), li, lp), shape=shape)
+        right = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(shape[1], shape[0]))
+        prod = (left @ right).tocsr()
+        prod.sort_indices()
+        assert np.array_equal(prod.indptr, scat["hyper_%s_indptr" % name]) and np.array_equal(prod.indices, scat["hyper_%s_indices" % name])
+        assert np.abs(prod.data - scat["hyper_%s_data" % name]).max() <= 1e-6 * np.abs(scat["hyper_%s_data" % name]).max()
+        x = scat["hyper_%s_X" % name]
+        y = O.spmm(lp, li, lv, O.spmm(rp, ri, rv, x))
+        assert rel_err(y, scat["hyper_%s_Y" % name]) < RTOL
