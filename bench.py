@@ -374,7 +374,10 @@ def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, prima
         model.train()  # HCCF.train calls model.train() every batch (HCCF.py:81): dropout on the learned incidence stays on
     else:
         model.eval()  # dropout off: the reference's HGNN_HD3 loop calls .eval() after its first batch (HGNN_HD3.py:186-204)
-    use_graph = world == 1 and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and small))
+    # the sharded step of an L2-resident workload is launch-bound too (~120 launches, 14 device-side barriers): captured the same
+    # way (symmetric-memory barriers, multicast stores and the NCCL all_reduce are ordinary stream work): C4 at N = 2 3.60 -> 1.85
+    # ms/step, N = 8 1.37 ms/step against 2.35 on one GPU.  HGR_DIST_GRAPH=0 keeps the sharded step eager.
+    use_graph = small and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and os.environ.get("HGR_DIST_GRAPH", "1") != "0"))
     optimizer = torch.optim.Adam(model.parameters(), lr=LR, fused=True, capturable=use_graph)
 
     # triples: the device sampler (csrc/sampler.cu: shuffled positives + rejection-sampled negatives, the body of
@@ -411,6 +414,8 @@ def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, prima
             # torch.unique's variable-length result is replaced by the fixed-size sorted-with-gaps form (loss_torch.unique_padded)
             graphed = trainer.GraphedStep(lambda a, b, c: trainer.train_step_hccf(model, optimizer, a, b, c, HCCF_TEMP, HCCF_SS_RATE,
                                                                                   HCCF_KEEP, static_shapes=True), b_local, dev)
+        elif world > 1:
+            graphed = trainer.GraphedStep(lambda a, b, c: hdist.train_step(model, optimizer, adj, a, b, c, REG, B), b_local, dev)
         else:
             graphed = trainer.GraphedTrainStep(model, optimizer, REG, B, b_local)
 
@@ -500,6 +505,11 @@ def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, prima
         for pool in adj._pools.values():
             pool.wait_events = None
     e2e_ms, _, _ = timed("e2e")
+    scale_parity = None
+    if world > 1 and adj.fused and primary:
+        from hypergraph_diffusion_for_recommendation_b200 import dist_check
+
+        scale_parity = dist_check.scale_check(adj, D)
     eval_info = run_eval(job, model, eval_inputs, part, adj, workload) if eval_inputs is not None else None
     if facade is not None and not primary:
         eval_info = run_eval_facade(job, model, facade)
@@ -553,6 +563,8 @@ def measure(job, workload, model_name, steps, warmup, cpu_steps, want_cpu, prima
                                      "device COO -> normalised CSR + split plan + work schedule (graph.build_norm_adj)")},
             "loss": [float(x) for x in losses.tolist()],
         }
+        if scale_parity is not None:
+            line["parity_at_scale"] = scale_parity
     del model, optimizer, sampler, adj, data, graphed, dev_triples, host_triples, eval_inputs, flush
     gc.collect()
     torch.cuda.empty_cache()
@@ -781,6 +793,9 @@ def run_ours(args):
             parity = dist_check.parity_check(job.rank, job.world, job.dev)
         if line is not None:
             line["extra_configs"] = extras
+            if parity is not None and line.get("parity_at_scale"):
+                parity["checks"].update({k: v for k, v in line["parity_at_scale"].items() if k != "multicast"})
+                parity["ok"] = all(parity["checks"].values())
             line["parity"] = parity
     if line is not None:
         emit(line)

@@ -36,20 +36,22 @@ class Epilogue(C.Structure):
         ("scale", C.c_float), ("scale_always", C.c_int32),
         ("pre", C.c_void_p),
         ("n_gather", C.c_int32), ("gather_out", C.c_void_p * HGR_MAX_GATHER), ("gather_row_offset", C.c_int64),
+        ("gather_mc", C.c_void_p),
     ]
 
 
 class Gather(C.Structure):
     """hgr_gather_t"""
-    _fields_ = [("n_gather", C.c_int32), ("out", C.c_void_p * HGR_MAX_GATHER), ("row_offset", C.c_int64)]
+    _fields_ = [("n_gather", C.c_int32), ("out", C.c_void_p * HGR_MAX_GATHER), ("row_offset", C.c_int64), ("mc", C.c_void_p)]
 
 
-def make_gather(ptrs, row_offset: int) -> Gather:
+def make_gather(ptrs, row_offset: int, mc: int = 0) -> Gather:
     g = Gather()
     g.n_gather = len(ptrs)
     for j, p in enumerate(ptrs):
         g.out[j] = int(p)
     g.row_offset = int(row_offset)
+    g.mc = int(mc) or None
     return g
 
 

@@ -61,6 +61,12 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
 }
 __device__ __forceinline__ float4 ld_ro_f4(const float4 *p) { return __ldg(p); }
 
+// One 16-byte store to a MULTICAST address: the NVSwitch delivers it to the copy of every GPU bound to the multicast object.
+__device__ __forceinline__ void st_multicast_f4(float4 *mc_addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 template <int WIDTH>
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 #pragma unroll

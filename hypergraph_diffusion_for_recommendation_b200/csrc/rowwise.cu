@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(kRwThreads) leaky_ln_bwd_kernel(const float4 *
             da.w = p.w > 0.f ? da.w : da.w * slope;
         }
         dpre[off] = da;
-        if (gt.n_gather > 0) {  // fused all-gather: the row into every rank's gathered table (peer-mapped memory)
+        if (gt.mc) {  // through the switch: one multimem store replicated into every rank's gathered table
+            st_multicast_f4(reinterpret_cast<float4 *>(gt.mc) + (gt.row_offset + row) * LPR + gl, da);
+        } else if (gt.n_gather > 0) {  // fused all-gather: the row into every rank's gathered table (peer-mapped memory)
             const int64_t goff = (gt.row_offset + row) * LPR + gl;
 #pragma unroll
             for (int p = 0; p < HGR_MAX_GATHER; ++p)  // constant indices keep gt in param space
@@ -150,6 +152,10 @@ __global__ void __launch_bounds__(kRwThreads) publish_rows_kernel(const float4 *
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
         const float4 v = ld_stream_f4(x + w);
+        if (gt.mc) {
+            st_multicast_f4(reinterpret_cast<float4 *>(gt.mc) + word_offset + w, v);
+            continue;
+        }
 #pragma unroll
         for (int p = 0; p < HGR_MAX_GATHER; ++p)
             if (p < gt.n_gather) reinterpret_cast<float4 *>(gt.out[p])[word_offset + w] = v;
@@ -161,6 +167,7 @@ static int check_gather(const hgr_gather_t *g) {
     HGR_REQUIRE(g->n_gather >= 0 && g->n_gather <= HGR_MAX_GATHER, "gather: n_gather %d out of range", g->n_gather);
     HGR_REQUIRE(g->row_offset >= 0, "gather: negative row_offset");
     for (int j = 0; j < g->n_gather; ++j) HGR_REQUIRE(g->out[j] && aligned16(g->out[j]), "gather: table %d NULL or misaligned", j);
+    HGR_REQUIRE(aligned16(g->mc), "gather: multicast address misaligned");
     return HGR_OK;
 }
 
@@ -181,6 +188,7 @@ int hgr_leaky_ln_bwd_f32(const float *pre, const float *dy, const float *gamma, 
     hgr_gather_t none;
     none.n_gather = 0;
     none.row_offset = 0;
+    none.mc = nullptr;
     return hgr_leaky_ln_bwd_gather_f32(pre, dy, gamma, ln_eps, use_leaky, leaky_slope, n_rows, D, dpre, dgamma, dbeta, partials, &none,
                                        stream);
 }
@@ -191,7 +199,7 @@ int hgr_publish_rows_f32(const float *x, int64_t n_rows, int32_t D, const hgr_ga
     HGR_REQUIRE(n_rows >= 0, "n_rows negative");
     int rc = check_gather(gather);
     if (rc) return rc;
-    if (n_rows == 0 || gather->n_gather == 0) return HGR_OK;
+    if (n_rows == 0 || (gather->n_gather == 0 && !gather->mc)) return HGR_OK;
     HGR_REQUIRE(x && aligned16(x), "x is NULL or misaligned");
     const int64_t n_words = n_rows * (D / 4);
     int64_t blocks = ceil_div(n_words, kRwThreads * 4);

@@ -221,7 +221,10 @@ __device__ __forceinline__ void finish_row(float4 acc, int64_t row, int gl, unsi
         acc.w *= ep.scale;
     }
     if (Y) reinterpret_cast<float4 *>(Y)[off] = acc;
-    if (ep.n_gather > 0) {
+    if (ep.gather_mc) {
+        // fused all-gather through the switch: one multimem store, replicated by NVSwitch into every rank's gathered table
+        st_multicast_f4(reinterpret_cast<float4 *>(ep.gather_mc) + (ep.gather_row_offset + row) * LPR + gl, acc);
+    } else if (ep.n_gather > 0) {
         // fused all-gather: the same row into the gathered table of every rank (peer-mapped memory; plain 128-bit
         // stores travel over NVLink as posted writes while the block moves on to its next rows)
         const int64_t goff = (ep.gather_row_offset + row) * LPR + gl;
@@ -414,6 +417,7 @@ static int check_epilogue(const hgr_epilogue_t *ep) {
     for (int j = 0; j < ep->n_gather; ++j)
         HGR_REQUIRE(ep->gather_out[j] && aligned16(ep->gather_out[j]), "epilogue: gather_out %d NULL or misaligned", j);
     HGR_REQUIRE(ep->gather_row_offset >= 0, "epilogue: negative gather_row_offset");
+    HGR_REQUIRE(aligned16(ep->gather_mc), "epilogue: gather_mc must be 16-byte aligned");
     return HGR_OK;
 }
 
@@ -495,7 +499,7 @@ static int spmm_impl(const hgr_csr_t *A, const float *X, float *Y, int32_t D, co
     rc = check_epilogue(epi);
     if (rc) return rc;
     HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
-    HGR_REQUIRE(A->n_rows == 0 || (X && (Y || (epi && epi->n_gather > 0))), "X or Y is NULL");
+    HGR_REQUIRE(A->n_rows == 0 || (X && (Y || (epi && (epi->n_gather > 0 || epi->gather_mc)))), "X or Y is NULL");
     HGR_REQUIRE(aligned16(X) && aligned16(Y), "X and Y must be 16-byte aligned");
     const size_t need = hgr_spmm_workspace_bytes(A, D);
     if (need > 0 && (ws == nullptr || ws_bytes < need))

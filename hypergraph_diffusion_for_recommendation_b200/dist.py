@@ -143,16 +143,16 @@ class LibhgrKernels:
         return ops.spmm_raw(block, x, ops.make_epilogue(**ep) if ep else None, no_local_out=no_local_out)
 
     @staticmethod
-    def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0):
+    def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0, gather_mc=0):
         from . import ops
 
-        return ops.leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs, gather_row_offset)
+        return ops.leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs, gather_row_offset, gather_mc)
 
     @staticmethod
-    def publish_rows(x, gather_ptrs, gather_row_offset):
+    def publish_rows(x, gather_ptrs, gather_row_offset, gather_mc=0):
         from . import ops
 
-        ops.publish_rows(x, gather_ptrs, gather_row_offset)
+        ops.publish_rows(x, gather_ptrs, gather_row_offset, gather_mc)
 
 
 class SymmetricPool:
@@ -164,13 +164,20 @@ class SymmetricPool:
     def __init__(self, n_glob: int, d: int, device, group, n_buffers: int = 4):
         import torch.distributed._symmetric_memory as symm_mem
 
-        self.bufs, self.hdls, self.ptrs = [], [], []
+        import os
+
+        self.bufs, self.hdls, self.ptrs, self.mc = [], [], [], []
+        use_mc = os.environ.get("HGR_MULTICAST", "1") != "0"
         for _ in range(n_buffers):
             t = symm_mem.empty((n_glob, d), dtype=torch.float32, device=device)
             h = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
             self.bufs.append(t)
             self.hdls.append(h)
             self.ptrs.append([int(p) for p in h.buffer_ptrs])
+            # NVSwitch multicast address of the slot (0 when the fabric / driver has no NVLS): one multimem.st per 16 bytes
+            # reaches every rank's copy, the unicast pointers stay as the fallback
+            self.mc.append(int(getattr(h, "multicast_ptr", 0) or 0) if use_mc else 0)
+        self.multicast = all(m != 0 for m in self.mc) and len(self.mc) > 0
         self.next = 0
         self.wait_events = None
 
@@ -278,7 +285,9 @@ class DistGraph:
         pool = self.pool(full_in.shape[1])
         k = pool.take()
         self._published.pop(k, None)  # the slot is being rewritten: forget what it held
-        ep = dict(ep or {}, gather_ptrs=pool.ptrs[k], gather_row_offset=self.rank * self.part.n_loc)
+        self.multicast = pool.multicast
+        ep = dict(ep or {}, gather_ptrs=pool.ptrs[k], gather_row_offset=self.rank * self.part.n_loc,
+                  gather_mc=pool.mc[k] if pool.multicast else 0)
         y = self.k.spmm(self.block, full_in, ep, no_local_out=not want_local)
         pool.barrier(k)  # every rank's rows have landed here, and every rank is done reading the slot's old contents
         if y is not None:
@@ -292,7 +301,8 @@ class DistGraph:
         pool = self.pool(dy.shape[1])
         k = pool.take()
         self._published.pop(k, None)
-        dz, dgamma, dbeta = self.k.leaky_ln_bwd(pre, dy, gamma, eps, slope, pool.ptrs[k], self.rank * self.part.n_loc)
+        dz, dgamma, dbeta = self.k.leaky_ln_bwd(pre, dy, gamma, eps, slope, pool.ptrs[k], self.rank * self.part.n_loc,
+                                                pool.mc[k] if pool.multicast else 0)
         pool.barrier(k)
         self._published[k] = (dz, dz._version)
         self.n_fused += 1
@@ -307,11 +317,11 @@ class DistGraph:
         if pool.wait_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc)
+            self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc, pool.mc[k] if pool.multicast else 0)
             e1.record()
             self.copy_events.append((e0, e1))
         else:
-            self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc)
+            self.k.publish_rows(x, pool.ptrs[k], self.rank * self.part.n_loc, pool.mc[k] if pool.multicast else 0)
         pool.barrier(k)
         self._published[k] = (x, x._version)
         self.n_published += 1

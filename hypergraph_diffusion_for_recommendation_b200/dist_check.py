@@ -152,3 +152,28 @@ def parity_check(rank: int, world: int, dev: torch.device, group=None) -> dict:
     checks = {k: bool(f) for k, f in zip(checks.keys(), flags.tolist())}
     return {"ok": all(checks.values()), "world": world, "checks": checks,
             "graph": "%d users x %d items x %d interactions, emb %d" % (N_USERS, N_ITEMS, N_TRAIN, D)}
+
+
+def scale_check(adj, d: int = 64, rounds: int = 3) -> dict:
+    """The same question at the size of the job itself: on THIS rank's block of the benchmark graph, a propagation whose input
+    table arrives through the fused exchange (peer / multicast stores issued by the producing kernel, device-side barrier) must
+    give the bits of the same propagation fed by an NCCL ``all_gather``.  A store that has not landed when a peer starts reading
+    shows up here as a differing row; every round uses fresh data and goes through a different slot of the pool."""
+    dev = adj.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + adj.rank)
+    ok_copy = ok_chain = True
+    with torch.no_grad():
+        for _ in range(rounds):
+            x = torch.randn(adj.part.n_loc, d, device=dev, generator=gen)
+            want1 = adj.k.spmm(adj.block, adj.all_gather(x))
+            want2 = adj.k.spmm(adj.block, adj.all_gather(want1))
+            full = adj.gathered(x)                                   # copy kernel -> every rank's table
+            _, got1 = adj.spmm_published(full, None, want_local=True)  # propagation epilogue -> every rank's table
+            got2 = adj.k.spmm(adj.block, adj.gathered(got1))
+            ok_copy = ok_copy and torch.equal(got1, want1)
+            ok_chain = ok_chain and torch.equal(got2, want2)
+    flags = torch.tensor([int(ok_copy), int(ok_chain)], device=dev, dtype=torch.int32)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=adj.group)
+    return {"job_graph_copy_gather_eq_nccl": bool(flags[0]), "job_graph_fused_gather_eq_nccl": bool(flags[1]),
+            "multicast": bool(getattr(adj, "multicast", False))}

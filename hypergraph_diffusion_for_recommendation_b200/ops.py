@@ -56,7 +56,7 @@ def _check_dense(x: torch.Tensor, rows: int, what: str) -> torch.Tensor:
 
 
 def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addends=(), scale=1.0, scale_always=False,
-              pre=None, gather_ptrs=(), gather_row_offset=0) -> _lib.Epilogue:
+              pre=None, gather_ptrs=(), gather_row_offset=0, gather_mc=0) -> _lib.Epilogue:
     ep = _lib.Epilogue()
     ep.use_leaky = 0 if slope is None else 1
     ep.leaky_slope = 0.0 if slope is None else float(slope)
@@ -71,20 +71,21 @@ def _epilogue(slope=None, gamma=None, beta=None, eps=1e-5, residual=None, addend
     for j, p in enumerate(gather_ptrs):
         ep.gather_out[j] = int(p)
     ep.gather_row_offset = int(gather_row_offset)
+    ep.gather_mc = int(gather_mc) or None  # NVSwitch multicast address of the gathered table (one multimem.st instead of world stores)
     return ep
 
 
 make_epilogue = _epilogue
 
 
-def publish_rows(x: torch.Tensor, gather_ptrs, gather_row_offset: int) -> None:
+def publish_rows(x: torch.Tensor, gather_ptrs, gather_row_offset: int, gather_mc: int = 0) -> None:
     """``hgr_publish_rows_f32``: store the owned rows ``x`` at ``gather_row_offset`` of every (peer-mapped) gathered table."""
     x = x.contiguous()
-    g = _lib.make_gather(gather_ptrs, gather_row_offset)
+    g = _lib.make_gather(gather_ptrs, gather_row_offset, gather_mc)
     _lib.check(_lib.lib().hgr_publish_rows_f32(x.data_ptr(), x.shape[0], x.shape[1], C.byref(g), _lib.stream_ptr()))
 
 
-def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0):
+def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0, gather_mc=0):
     """Backward of ``LayerNorm(leaky_relu(pre)) * gamma + beta`` (hgr_leaky_ln_bwd_f32): returns
     ``(dpre, dgamma, dbeta)``; ``gamma is None`` means no LayerNorm.  ``gather_ptrs``: also publish the ``dpre`` rows into
     every rank's gathered table (hgr_leaky_ln_bwd_gather_f32)."""
@@ -94,7 +95,7 @@ def leaky_ln_bwd(pre, dy, gamma, eps, slope, gather_ptrs=(), gather_row_offset=0
     if gamma is not None:
         dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
         parts = torch.empty((_lib.lib().hgr_ln_bwd_partial_rows(dy.shape[0]), 2, d), dtype=torch.float32, device=dy.device)
-    g = _lib.make_gather(gather_ptrs, gather_row_offset)
+    g = _lib.make_gather(gather_ptrs, gather_row_offset, gather_mc)
     _lib.check(_lib.lib().hgr_leaky_ln_bwd_gather_f32(pre.data_ptr(), dy.data_ptr(), _lib.ptr(gamma), float(eps), 0 if slope is None else 1,
                                                       0.0 if slope is None else float(slope), dy.shape[0], d, dz.data_ptr(),
                                                       _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(parts), C.byref(g), _lib.stream_ptr()))

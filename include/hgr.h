@@ -102,6 +102,10 @@ typedef struct {
     int32_t n_gather;
     float *gather_out[HGR_MAX_GATHER];
     int64_t gather_row_offset;
+    /* NVSwitch multicast form of the same exchange: the MULTICAST address of the gathered table (one virtual address bound to
+     * every rank's copy, NVLS).  When non-NULL a row is published with ONE multimem.st per 16 bytes and the switch replicates
+     * it to all ranks, instead of n_gather unicast stores (1/world of the egress).  gather_out / n_gather are then ignored. */
+    float *gather_mc;
 } hgr_epilogue_t;
 
 /* Y[n_rows, D] = epilogue(A . X[n_cols, D]).  Replaces torch.sparse.mm(adj, X)
@@ -152,6 +156,7 @@ typedef struct {
     int32_t n_gather;
     float *out[HGR_MAX_GATHER];
     int64_t row_offset;
+    float *mc; /* multicast address of the gathered table, or NULL (see hgr_epilogue_t::gather_mc) */
 } hgr_gather_t;
 
 /* hgr_leaky_ln_bwd_f32 whose dpre rows -- the input of the sharded backward propagation that always follows
