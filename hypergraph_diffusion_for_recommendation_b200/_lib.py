@@ -85,6 +85,7 @@ SIGNATURES = {
     "hgr_bpr_l2_workspace_bytes": (_SZ, [_I64]),
     "hgr_bpr_l2_fwd_f32": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, _VP, _VP, _I64, _F32, _F32, _VP, _VP, _SZ, _VP, _VP]),
     "hgr_rank_metrics": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "hgr_drop_edges_f32": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _I64, _F32, C.c_uint64, _VP, _VP, _VP, _I32, _VP, _VP]),
     "hgr_rank_metric_sums": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "hgr_bpr_sample": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP, _VP, _I32, C.c_uint64, C.c_uint64, _VP, _VP, _VP, _VP, _VP]),
     "hgr_ssl_workspace_bytes": (_SZ, [_I64, _I32]),

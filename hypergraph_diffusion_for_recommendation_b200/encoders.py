@@ -174,28 +174,58 @@ class HGCNConv(nn.Module):
                           1e-5 if ln is None else ln.eps)
 
 
+def drop_edges(adj: DeviceCSR, keep: float, mask: torch.Tensor | None = None, seed: int | None = None,
+               step: torch.Tensor | None = None) -> DeviceCSR:
+    """``hgr.drop_edges(adj, keep, mask)`` (SURVEY.md 8b seam 6) on ``hgr_drop_edges_f32``: the matrix with THIS sparsity
+    pattern whose entries are kept with probability ``keep`` and rescaled by ``1 / keep`` (dropped ones become explicit zeros), plus
+    the same for its transpose (what the backward propagation reads) -- two launches, no sort, no compaction.
+    ``mask``: uniform numbers of ``torch.rand(nnz)`` (any device) to replay the reference's random stream, entry for entry;
+    ``None``: Philox on the device keyed by ``seed`` and the entry's coordinates; ``step`` (a one-element int64 CUDA tensor) is mixed
+    into the seed when the kernel RUNS, so a captured CUDA graph draws a new mask at every replay."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.lib()
+    nnz = adj._nnz()
+    dev = adj.device
+    vals = torch.empty(nnz, dtype=torch.float32, device=dev)
+    rand = None if mask is None else mask.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    sd = 0 if seed is None else int(seed) & ((1 << 64) - 1)
+
+    def run(mirror, pos, out):
+        _lib.check(lib.hgr_drop_edges_f32(adj.indptr.data_ptr(), adj.indices.data_ptr(), adj.values.data_ptr(), adj.shape[0], adj.shape[1],
+                                          nnz, float(keep), C.c_uint64(sd), _lib.ptr(step), _lib.ptr(rand), _lib.ptr(pos), mirror,
+                                          out.data_ptr(), _lib.stream_ptr()))
+
+    run(0, None, vals)
+    if not (adj.symmetric or getattr(adj, "_tperm", None) is not None) or adj.shape[0] != adj.shape[1]:
+        return adj.with_values(vals)  # the transpose of a general matrix is built on demand (DeviceCSR.t)
+    t_vals = torch.empty(nnz, dtype=torch.float32, device=dev)
+    run(1, adj.transpose_permutation() if rand is not None else None, t_vals)
+    return adj.with_values(vals, t_vals)
+
+
 class SpAdjDropEdge(nn.Module):
-    """Bernoulli edge dropout with the reference's CPU random stream (``torch.rand(nnz)`` on the host
-    generator), so a seeded run keeps and rescales exactly the same edges."""
+    """Bernoulli edge dropout (``drop_edges``).  Default: the reference's CPU random stream (``torch.rand(nnz)`` on the host
+    generator, HCCF.py:224), so a seeded run keeps and rescales exactly the same edges; ``rand`` = uniform numbers drawn elsewhere;
+    ``seed`` = draw on the device with Philox instead (no host work, no upload)."""
 
     def __init__(self):
         super(SpAdjDropEdge, self).__init__()
 
-    def forward(self, adj: DeviceCSR, keepRate, rand=None):
+    def forward(self, adj: DeviceCSR, keepRate, rand=None, seed=None, step=None):
         if keepRate == 1.0:
             return adj
-        nnz = adj._nnz()
+        if rand is None and seed is None:
+            rand = torch.rand(adj._nnz())
+        if adj.shape[0] == adj.shape[1] and (adj.symmetric or getattr(adj, "_tperm", None) is not None):
+            return drop_edges(adj, keepRate, rand, seed, step)
+        # rectangular / asymmetric matrices: compacted like the reference does (their transpose is rebuilt by DeviceCSR.t)
         if rand is None:
-            rand = torch.rand(nnz)
-        mask = ((rand + keepRate).floor()).type(torch.bool).to(adj.device, non_blocking=True)
-        # tensor / tensor is a true IEEE division (the scalar overload multiplies by a reciprocal on CUDA),
-        # which keeps the rescaled values bit-identical to the reference's CPU `vals[mask] / keepRate`
+            rand = torch.rand(adj._nnz(), device=adj.device)
+        mask = ((rand.to(adj.device) + keepRate).floor()).type(torch.bool)
         keep = torch.full((), float(keepRate), dtype=torch.float32, device=adj.device)
-        if adj.symmetric or getattr(adj, "_tperm", None) is not None:
-            # the normalised adjacency: keep its pattern and split plan, zero the dropped values; the transpose the
-            # backward pass needs is the same pattern with permuted values -- no sort, no host round trip per batch
-            vals = torch.where(mask, adj.values / keep, torch.zeros((), dtype=torch.float32, device=adj.device))
-            return adj.with_values(vals, vals[adj.transpose_permutation()])
         rows = torch.repeat_interleave(torch.arange(adj.shape[0], device=adj.device), adj.indptr[1:] - adj.indptr[:-1])
         counts = torch.bincount(rows[mask], minlength=adj.shape[0])
         indptr = torch.zeros(adj.shape[0] + 1, dtype=torch.int64, device=adj.device)
@@ -422,19 +452,14 @@ class HGNNLayer(nn.Module):
         self.act = nn.LeakyReLU(negative_slope=leaky)
 
     def forward(self, adj, embeds):
-        # adj [n, hyper_dim] dense learned incidence, embeds [n, D]: two tall-and-skinny products on libhgr
-        # (csrc/hyperedge.cu); widths the kernels do not cover stay on the library GEMM
-        if ops.hyperedge_supported(adj, embeds):
-            return ops.hyperedge(adj, embeds)
-        return torch.mm(adj, torch.mm(adj.T, embeds))
+        # adj [n, hyper_dim] dense learned incidence, embeds [n, D]: two tall-and-skinny products on libhgr (csrc/hyperedge.cu)
+        return ops.hyperedge(adj, embeds)  # raises for widths the kernels do not cover: there is no library fallback
 
 
 def _dense_incidence(emb, w):
     """``emb @ w`` (HCCF.py:178-179): tall-and-skinny in the forward pass, and its weight gradient ``emb.T @ dH`` contracts
-    over all nodes -- libhgr kernels where the widths allow, the library GEMM otherwise."""
-    if ops.tall_times_small_supported(emb, w):
-        return ops.tall_times_small(emb, w)
-    return emb @ w
+    over all nodes -- libhgr kernels (widths 32 / 64 / 128; anything else raises, there is no library fallback)."""
+    return ops.tall_times_small(emb, w)
 
 
 class HCCFEncoder(nn.Module):
@@ -472,8 +497,18 @@ class HCCFEncoder(nn.Module):
             'item_w': nn.Parameter(initializer(torch.empty(self.latent_size, self.n_edges))),
         })
 
+    def _drop_step(self):
+        """Device-side step counter mixed into the Philox seed of the edge-drop kernel (advanced once per forward by a captured
+        add, so a replayed CUDA graph draws new masks every step)."""
+        ctr = getattr(self, "_drop_ctr", None)
+        if ctr is None:
+            ctr = self._drop_ctr = torch.zeros(1, dtype=torch.int64, device=self.sparse_norm_adj.device)
+            self._drop_seed = int(torch.initial_seed()) & 0x7fffffff
+        ctr += 1
+        return ctr
+
     def forward(self, keep_rate=0.5, device_rng=False):
-        """``device_rng``: draw each layer's edge-drop mask with ``torch.rand(nnz, device=cuda)`` instead of the reference's
+        """``device_rng``: draw each layer's edge-drop mask with Philox inside ``hgr_drop_edges_f32`` instead of the reference's
         CPU ``torch.rand(nnz)`` + upload (HCCF.py:217-226); the default replays the reference's CPU random stream."""
         n_users = self.data.n_users
         embeddings = torch.cat([self.embedding_dict['user_emb'], self.embedding_dict['item_emb']], 0)
@@ -482,9 +517,10 @@ class HCCFEncoder(nn.Module):
         hgnn_hidden = []
         hyper_uu = _dense_incidence(self.embedding_dict['user_emb'], self.embedding_dict['user_w'])
         hyper_ii = _dense_incidence(self.embedding_dict['item_emb'], self.embedding_dict['item_w'])
+        step = self._drop_step() if device_rng and keep_rate != 1.0 else None
         for i in range(self.n_layers):
-            rand = torch.rand(self.sparse_norm_adj._nnz(), device=self.sparse_norm_adj.device) if device_rng and keep_rate != 1.0 else None
-            gcn_emb = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate, rand), hidden[-1])
+            gcn_emb = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate, None, self._drop_seed + i if step is not None else None, step),
+                                    hidden[-1])
             hyper_uemb = self.hgnnlayer(self.drop_out(hyper_uu), hidden[-1][:n_users])
             hyper_iemb = self.hgnnlayer(self.drop_out(hyper_ii), hidden[-1][n_users:])
             gcn_hidden += [gcn_emb]
@@ -539,10 +575,8 @@ class SHTEncoder(nn.Module):
         return ops.spmm(adj, embeds)
 
     def hgnnLayer(self, embeds, hyper):
-        small = hyper.T @ hyper  # [D, D]
-        if ops.tall_times_small_supported(embeds, small):
-            return ops.tall_times_small(embeds, small)
-        return embeds @ small
+        small = hyper.T @ hyper  # [D, D]: a D x D product of two parameter matrices, not a pass over the nodes
+        return ops.tall_times_small(embeds, small)
 
     def forward(self):
         embeds = torch.concat([self.uEmbeds, self.iEmbeds], dim=0)

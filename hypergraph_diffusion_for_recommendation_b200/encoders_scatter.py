@@ -112,11 +112,12 @@ class HCCFDiffusionEncoder(HCCFEncoder):
         hidden = [torch.cat([emb['user_emb'], emb['item_emb']], 0)]
         gcn_hidden, hgnn_hidden = [], []
         with torch.no_grad():  # only the sign pattern of E W is used (nonzero(H > 0) passes no gradient, HCCF_diffusion.py:384)
-            hyper_uu, hyper_ii = emb['user_emb'] @ emb['user_w'], emb['item_emb'] @ emb['item_w']
-        for _ in range(self.n_layers):
+            hyper_uu = ops.rows_times_small(emb['user_emb'].contiguous(), None, emb['user_w'].contiguous())
+            hyper_ii = ops.rows_times_small(emb['item_emb'].contiguous(), None, emb['item_w'].contiguous())
+        step = self._drop_step() if device_rng and keep_rate != 1.0 else None
+        for layer in range(self.n_layers):
             cur = hidden[-1]
-            rand = torch.rand(self.sparse_norm_adj._nnz(), device=cur.device) if device_rng and keep_rate != 1.0 else None
-            gcn = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate, rand), cur)
+            gcn = self.gcnlayer(self.edgeDropper(self.sparse_norm_adj, keep_rate, None, self._drop_seed + layer if step is not None else None, step), cur)
             bu = (self.drop_out(hyper_uu) > 0).to(torch.float32)
             bi = (self.drop_out(hyper_ii) > 0).to(torch.float32)
             hyp = torch.cat([self.edhnnlayer(cur[:n_users], bu, self.edhnn_user_n), self.edhnnlayer(cur[n_users:], bi, self.edhnn_item_n)], 0)

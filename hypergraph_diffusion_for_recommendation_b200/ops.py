@@ -466,8 +466,8 @@ def tall_times_small(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 class _Linear(torch.autograd.Function):
     """``[relu](F.linear(x, weight, bias))`` for tall inputs.  Forward: one pass of the rows x small-matrix kernel with the bias
     (and the ReLU) in its epilogue, instead of cuBLAS sgemm + bias kernel + ReLU kernel (0.37 + 0.40 + 0.11 ms for 1.5 M rows of
-    64).  Backward: ``dx`` on the library GEMM, the weight gradient ``dy.T @ x`` -- a contraction over ALL rows that cuBLAS runs as
-    a few-block SIMT kernel (0.84 ms) -- on the tall-skinny reduce of csrc/hyperedge.cu."""
+    64).  Backward: ``dx = dy W`` on the same rows x small-matrix kernel, the weight gradient ``dy.T @ x`` -- a contraction over ALL
+    rows that cuBLAS runs as a few-block SIMT kernel (0.84 ms) -- on the tall-skinny reduce of csrc/hyperedge.cu.  No library GEMM."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
@@ -483,17 +483,19 @@ class _Linear(torch.autograd.Function):
         dy = dy.contiguous()
         if ctx.relu:
             dy = dy * (y > 0)
-        dx = dy @ weight if ctx.needs_input_grad[0] else None
+        dx = rows_times_small(dy, None, weight.contiguous()) if ctx.needs_input_grad[0] else None  # dy [n, out] x weight [out, in]
         dw = tall_skinny_tn(dy, x) if ctx.needs_input_grad[1] else None
         db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool = False) -> torch.Tensor:
-    """Drop-in for ``nn.Linear.forward`` (``relu=True``: followed by ``F.relu``) on ``[rows, in]`` float32 CUDA inputs whose
-    widths the libhgr kernels cover (out in {32, 64, 128, 256}, in in {32, 64, 128}); other shapes go through ``F.linear``."""
-    if (x.is_cuda and x.dim() == 2 and x.dtype == weight.dtype == torch.float32 and weight.shape[0] in (32, 64, 128, 256)
-            and weight.shape[1] in (32, 64, 128) and x.shape[0] >= 4096):
-        return _Linear.apply(x, weight, bias, relu)
-    y = torch.nn.functional.linear(x, weight, bias)
-    return torch.relu(y) if relu else y
+    """Drop-in for ``nn.Linear.forward`` (``relu=True``: followed by ``F.relu``) on ``[rows, in]`` float32 CUDA inputs:
+    out in {32, 64, 128, 256}, in in {32, 64, 128} -- the widths of every Linear on the hot path (MLP / lin_in of the ED-HNN
+    blocks).  Anything else raises: there is no library fallback behind it."""
+    if not x.is_cuda:
+        raise _lib.HgrError("linear: input must be a CUDA tensor (no CPU path)")
+    if not (x.dim() == 2 and x.dtype == weight.dtype == torch.float32 and weight.shape[0] in (32, 64, 128, 256)
+            and weight.shape[1] in (32, 64, 128) and x.shape[1] == weight.shape[1]):
+        raise ValueError("linear: need float32 x [rows, 32|64|128] and weight [32|64|128|256, in], got %s and %s" % (tuple(x.shape), tuple(weight.shape)))
+    return _Linear.apply(x, weight, bias, relu)

@@ -206,6 +206,18 @@ int hgr_csr_scale(const int64_t *indptr, const int32_t *indices, float *values, 
                   const float *col_scale, hgr_stream_t stream);
 
 
+/* Bernoulli edge dropout with the pattern kept: SpAdjDropEdge.forward (model/graph/HCCF.py:217-226; same class in HGNN_HD3.py,
+ * HGNN_HD4.py, HCCF_diffusion.py).  out[p] = keep(p) ? values[p] / keep : 0 (true division), keep(p) = floor(u + keep) != 0 in
+ * fp32 with u = rand[rand_pos ? rand_pos[p] : p] (the caller's uniform numbers: replay of the reference's torch.rand(nnz) stream)
+ * or, with rand == NULL, a 24-bit uniform from Philox4x32-10(seed) keyed by the entry's coordinates.  mirror != 0 keys entry
+ * (r, c) with (c, r): the values of the TRANSPOSED dropped matrix on the same structurally symmetric pattern (in replay mode pass
+ * the transpose permutation as rand_pos instead).  Dropped entries stay as explicit zeros: row sums are bit-identical to the
+ * compacted matrix, and the split plan / schedule of the propagation kernel are reused.  seed_dev (optional, DEVICE uint64): a step
+ * counter mixed into the seed at run time, so a captured CUDA graph draws a new mask at every replay. */
+int hgr_drop_edges_f32(const int64_t *indptr, const int32_t *indices, const float *values, int32_t n_rows, int64_t n_cols, int64_t nnz,
+                       float keep, uint64_t seed, const uint64_t *seed_dev, const float *rand, const int64_t *rand_pos, int32_t mirror,
+                       float *out, hgr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Dense learned-hyperedge propagation of HCCF: HGNNLayer.forward (model/graph/HCCF.py:206-211),
  *   edge_embeds = torch.mm(adj.T, embeds);  hyper_embeds = torch.mm(adj, edge_embeds)

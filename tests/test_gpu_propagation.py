@@ -477,3 +477,35 @@ def test_sgl_encoder_on_the_data_facade_with_repeated_training_pairs(hgr):
     assert np.abs(dv - want).max() < 1e-6
     ue, ie = enc(adj)
     assert ue.shape == (data.n_users, 64) and torch.isfinite(ue).all() and torch.isfinite(ie).all()
+
+
+def test_drop_edges_philox_mask_is_a_consistent_transpose_pair_and_changes_with_the_step(hgr, adj):
+    """``hgr_drop_edges_f32`` without host random numbers (SURVEY 8b seam 6): keep rate, rescaling, the mirrored launch really is
+    the transpose of the dropped matrix, same seed -> same mask, and the device-side step counter gives a new mask."""
+    keep = 0.7
+    d1 = hgr.enc.drop_edges(adj, keep, seed=11)
+    ip, ix, dv = d1.to_host()
+    full = adj.to_host()[2]
+    kept = dv != 0
+    assert abs(kept.mean() - keep) < 0.05
+    assert np.array_equal(bits(dv[kept]), bits((full[kept] / np.float32(keep)).astype(np.float32)))  # true division of the kept values
+    n = adj.shape[0]
+    import scipy.sparse as sp
+
+    a = sp.csr_matrix((dv, ix, ip), shape=(n, n))
+    tp, ti, tv = d1.t().to_host()
+    at = sp.csr_matrix((tv, ti, tp), shape=(n, n))
+    assert (a.T != at).nnz == 0                                            # mirror launch == transpose of the dropped matrix
+    assert (a != a.T).nnz > 0                                              # the two directions of an edge are dropped independently
+    d2 = hgr.enc.drop_edges(adj, keep, seed=11)
+    assert np.array_equal(bits(d2.to_host()[2]), bits(dv))                 # counter-based: reproducible
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    s0 = hgr.enc.drop_edges(adj, keep, seed=11, step=step).to_host()[2]
+    step += 1
+    s1 = hgr.enc.drop_edges(adj, keep, seed=11, step=step).to_host()[2]
+    assert np.array_equal(bits(s0), bits(dv)) and not np.array_equal(bits(s0), bits(s1))
+    x = cuda(np.random.default_rng(0).standard_normal((n, 64)).astype(np.float32)).requires_grad_(True)
+    y = hgr.ops.spmm(d1, x)
+    y.sum().backward()
+    want = np.asarray(at @ np.ones((n, 64), np.float32))                   # d/dx sum(A x) = A^T 1
+    assert rel_err(x.grad, want) < RTOL
