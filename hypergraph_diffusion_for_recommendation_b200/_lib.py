@@ -77,6 +77,8 @@ SIGNATURES = {
     "hgr_tall_skinny_tn_f32": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _SZ, _VP]),
     "hgr_rows_times_small_f32": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, _I64, _VP, _VP]),
     "hgr_rows_times_small_bias_f32": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, _I64, _VP, _VP, _I32, _VP]),
+    "hgr_rows_times_small_gather_f32": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, _I64, _VP, _VP, _I32, C.POINTER(Gather), _VP]),
+    "hgr_add_rows_f32": (C.c_int, [_VP, _VP, _I64, _I32, _VP, C.POINTER(Gather), _VP]),
     "hgr_build_csr_workspace_bytes": (_SZ, [_I64]),
     "hgr_coo_to_csr": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "hgr_bipartite_to_csr": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -912,12 +912,13 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
         if (sub < 1) sub = 1;
         p.f_sub_tiles = (int)ceil_div(p.n_tiles, sub);
         p.f_sub = (int)ceil_div(p.n_tiles, p.f_sub_tiles);
-        // candidate slots: every (sub-range, column half, user) owns `cap` of them, ~768 per user in all (1 536 for K > 32); a list
-        // that overflows sends its user to the exact brute-force kernel.  With ~4 K candidates per user spread over the parts the
-        // expected load of a list is 4 K / parts.
-        const int parts = p.f_sub * EV_CSPLIT;
-        int cap = ((K <= 32 ? 768 : 1536) / parts) / 8 * 8;
-        if (cap < 16) cap = 16;
+        // candidate slots: every (sub-range, column half, user) owns `cap` of them.  A user keeps ~4 K candidates in all (the
+        // threshold comes from a 1 / 4 sample), but NOT spread evenly: with ids handed out in order of first appearance the
+        // popular items share the first tiles, so a single list must be able to take the user's whole set (4 K and some).  A
+        // list that still overflows sends its user to the exact brute-force kernel.  parts * n_test_pad <= ~1.2 M lists by
+        // construction (EV_CELLS_PER_SM), i.e. < 1 GB of slots at K = 20.
+        int cap = (4 * K + 7) / 8 * 8;
+        if (cap < 64) cap = 64;
         if (cap > 512) cap = 512;
         p.cap = cap;
     }

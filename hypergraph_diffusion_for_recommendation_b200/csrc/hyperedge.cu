@@ -12,6 +12,8 @@
 //     dT = H^T dY,   dE = H dT,   dH = [dY | E] [T^T ; dT^T]
 // Arithmetic is fp32 FMA throughout; results agree with torch.mm to rounding (the summation order differs), tolerance
 // 1e-5 relative in the tests.
+#include <string.h>
+
 #include "hgr_internal.cuh"
 
 namespace hgr {
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const floa
                                                                       const float *__restrict__ A2, int K2,
                                                                       const float *__restrict__ B, int64_t n,
                                                                       float *__restrict__ Y, const float *__restrict__ bias,
-                                                                      int relu) {
+                                                                      int relu, hgr_gather_t gt) {
     constexpr int TX = N / 4, TY = kHeThreads / TX, RPT = TR / TY;  // rows per thread
     static_assert(RPT >= 1, "tile shorter than the thread layout");
     extern __shared__ __align__(16) float he_smem[];
@@ -180,7 +182,18 @@ __global__ void __launch_bounds__(kHeThreads) rows_times_small_kernel(const floa
             const int64_t r = r0 + ty + TY * i;
             float4 o = make_float4(acc[i].x + bv.x, acc[i].y + bv.y, acc[i].z + bv.z, acc[i].w + bv.w);
             if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-            if (r < n) reinterpret_cast<float4 *>(Y + r * N)[tx] = o;
+            if (r < n) {
+                reinterpret_cast<float4 *>(Y + r * N)[tx] = o;
+                // sharded training: the finished row also goes into every rank's gathered table (the propagation that consumes
+                // this layer's output finds it there: no separate exchange)
+                if (gt.mc) {
+                    st_multicast_f4(reinterpret_cast<float4 *>(gt.mc) + (gt.row_offset + r) * TX + tx, o);
+                } else if (gt.n_gather > 0) {
+#pragma unroll
+                    for (int p = 0; p < HGR_MAX_GATHER; ++p)
+                        if (p < gt.n_gather) reinterpret_cast<float4 *>(gt.out[p])[(gt.row_offset + r) * TX + tx] = o;
+                }
+            }
         }
         __syncthreads();  // the buffer just read is the target of the prefetch after next
     }
@@ -265,7 +278,20 @@ int hgr_rows_times_small_f32(const float *A1, int32_t K1, const float *A2, int32
 
 int hgr_rows_times_small_bias_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
                                   float *Y, const float *bias, int32_t relu, hgr_stream_t stream) {
+    return hgr_rows_times_small_gather_f32(A1, K1, A2, K2, B, N, n, Y, bias, relu, nullptr, stream);
+}
+
+int hgr_rows_times_small_gather_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
+                                    float *Y, const float *bias, int32_t relu, const hgr_gather_t *gather, hgr_stream_t stream) {
     using namespace hgr;
+    hgr_gather_t gt;
+    memset(&gt, 0, sizeof(gt));
+    if (gather) {
+        gt = *gather;
+        HGR_REQUIRE(gt.n_gather >= 0 && gt.n_gather <= HGR_MAX_GATHER && gt.row_offset >= 0, "gather: bad n_gather / row_offset");
+        for (int j = 0; j < gt.n_gather; ++j) HGR_REQUIRE(gt.out[j] && aligned16(gt.out[j]), "gather: table %d NULL or misaligned", j);
+        HGR_REQUIRE(aligned16(gt.mc), "gather: multicast address misaligned");
+    }
     HGR_REQUIRE(aligned16(bias), "bias must be 16-byte aligned");
     HGR_REQUIRE(n >= 0, "n negative");
     HGR_REQUIRE(K1 > 0 && K1 % 4 == 0 && K2 >= 0 && K2 % 4 == 0 && K1 + K2 <= 256, "K1 = %d, K2 = %d unsupported", K1, K2);
@@ -284,7 +310,7 @@ int hgr_rows_times_small_bias_f32(const float *A1, int32_t K1, const float *A2, 
 #define HGR_RTS(NN, TT)                                                                                                          \
     do {                                                                                                                         \
         HGR_CUDA_OK(cudaFuncSetAttribute(rows_times_small_kernel<NN, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rows_times_small_kernel<NN, TT><<<(unsigned)blocks, kHeThreads, smem, st>>>(A1, K1, A2, K2, B, n, Y, bias, relu);         \
+        rows_times_small_kernel<NN, TT><<<(unsigned)blocks, kHeThreads, smem, st>>>(A1, K1, A2, K2, B, n, Y, bias, relu, gt);     \
     } while (0)
     if (TR == 64) {
         switch (N) {

@@ -162,6 +162,25 @@ __global__ void __launch_bounds__(kRwThreads) publish_rows_kernel(const float4 *
     }
 }
 
+// out = a + b over 128-bit words, the sum also stored into every rank's gathered table (the "+ res" that ends an encoder layer,
+// model/graph/HGNN_HD3.py:419: its result is the input of the next sharded propagation)
+__global__ void __launch_bounds__(kRwThreads) add_rows_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, float4 *__restrict__ out,
+                                                               int64_t n_words, int64_t word_offset, hgr_gather_t gt) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        const float4 x = ld_stream_f4(a + w), y = ld_stream_f4(b + w);
+        const float4 v = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        out[w] = v;
+        if (gt.mc) {
+            st_multicast_f4(reinterpret_cast<float4 *>(gt.mc) + word_offset + w, v);
+        } else {
+#pragma unroll
+            for (int p = 0; p < HGR_MAX_GATHER; ++p)
+                if (p < gt.n_gather) reinterpret_cast<float4 *>(gt.out[p])[word_offset + w] = v;
+        }
+    }
+}
+
 static int check_gather(const hgr_gather_t *g) {
     HGR_REQUIRE(g != nullptr, "gather is NULL");
     HGR_REQUIRE(g->n_gather >= 0 && g->n_gather <= HGR_MAX_GATHER, "gather: n_gather %d out of range", g->n_gather);
@@ -207,6 +226,29 @@ int hgr_publish_rows_f32(const float *x, int64_t n_rows, int32_t D, const hgr_ga
     publish_rows_kernel<<<(unsigned)blocks, kRwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(x), n_words,
                                                                                  gather->row_offset * (D / 4), *gather);
     HGR_LAUNCH_OK("publish_rows_kernel");
+    return HGR_OK;
+}
+
+int hgr_add_rows_f32(const float *a, const float *b, int64_t n_rows, int32_t D, float *out, const hgr_gather_t *gather, hgr_stream_t stream) {
+    using namespace hgr;
+    HGR_REQUIRE(D > 0 && D % 4 == 0 && n_rows >= 0, "bad n_rows / D");
+    hgr_gather_t gt;
+    gt.n_gather = 0;
+    gt.row_offset = 0;
+    gt.mc = nullptr;
+    if (gather) {
+        int rc = check_gather(gather);
+        if (rc) return rc;
+        gt = *gather;
+    }
+    if (n_rows == 0) return HGR_OK;
+    HGR_REQUIRE(a && b && out && aligned16(a) && aligned16(b) && aligned16(out), "operand NULL or misaligned");
+    const int64_t n_words = n_rows * (D / 4);
+    int64_t blocks = ceil_div(n_words, kRwThreads * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    add_rows_kernel<<<(unsigned)blocks, kRwThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
+                                                                             reinterpret_cast<float4 *>(out), n_words, gt.row_offset * (D / 4), gt);
+    HGR_LAUNCH_OK("add_rows_kernel");
     return HGR_OK;
 }
 

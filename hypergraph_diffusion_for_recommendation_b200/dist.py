@@ -308,6 +308,21 @@ class DistGraph:
         self.n_fused += 1
         return dz, dgamma, dbeta, pool.bufs[k]
 
+    def publish_by(self, d: int, produce):
+        """Let a row-wise kernel that is NOT a propagation carry the exchange: ``produce(gather)`` runs it with
+        ``gather = (peer pointers, row offset, multicast pointer)`` of a free pool slot and returns its ``[n_loc, d]`` output, whose
+        gathered copy is then registered like a propagation's (``ops.linear(publish=...)``, ``ops.add_rows(publish=...)``)."""
+        pool = self.pool(d)
+        if pool is None:
+            return produce(None)
+        k = pool.take()
+        self._published.pop(k, None)
+        y = produce((pool.ptrs[k], self.rank * self.part.n_loc, pool.mc[k] if pool.multicast else 0))
+        pool.barrier(k)
+        self._published[k] = (y, y._version)
+        self.n_fused += 1
+        return y
+
     def publish(self, x: torch.Tensor) -> torch.Tensor:
         """Rows that do not come out of a libhgr kernel (dense layers, elementwise ops): one copy kernel stores them into
         every rank's table over NVLink (757 GB/s measured at 2 ranks against 428 GB/s for the NCCL all_gather)."""

@@ -389,7 +389,9 @@ class EquivSetGNN(nn.Module):
 
     def forward(self, x, sparse_norm_adj, n_nodes=None, ui_adj=None, act=True):
         x = self.dropout(x)
-        x = ops.linear(x, self.lin_in.weight, self.lin_in.bias, relu=True)
+        # (sharded graph: the rows of this Linear are the input of the first propagation -- its epilogue publishes them)
+        x = ops.linear(x, self.lin_in.weight, self.lin_in.bias, relu=True,
+                       publish=sparse_norm_adj if ops._sharded(sparse_norm_adj) and not (self.training and self.dropout.p > 0) else None)
         x0 = x
         for i in range(self.nlayer):
             x = self.dropout(x)
@@ -429,7 +431,9 @@ class LocalAwareEncoder(nn.Module):
         res = ego_embeddings
         for k in range(self.layers):
             if k != self.layers - 1:
-                ego_embeddings = self.edhnn_layers[k](ego_embeddings, sparse_norm_adj, self.edhnn_ui_n, None) + res
+                # "+ res" on hgr_add_rows_f32; when the graph is sharded the sum reaches every rank's table from the same kernel
+                ego_embeddings = ops.add_rows(self.edhnn_layers[k](ego_embeddings, sparse_norm_adj, self.edhnn_ui_n, None), res,
+                                              publish=self.sparse_norm_adj if ops._sharded(self.sparse_norm_adj) else None)
             else:
                 # lns[k](hgcn(A, ego, act=False)) + res in one fused two-stage propagation; like the
                 # reference this last layer always uses the un-dropped adjacency

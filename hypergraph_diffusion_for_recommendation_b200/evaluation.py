@@ -232,14 +232,12 @@ def ranking_evaluation_device(truth_indptr, truth_items, rec_ids: torch.Tensor, 
     dev = rec_ids.device
     rec_ids = rec_ids.to(torch.int32).contiguous()
     n_users, k = rec_ids.shape
-    tp = torch.as_tensor(np.asarray(truth_indptr, dtype=np.int64))
-    ti = torch.as_tensor(np.asarray(truth_items, dtype=np.int64))
-    n_truth = (tp[1:] - tp[:-1])
-    # sort every truth row ascending (row id is the major key)
-    rows = torch.repeat_interleave(torch.arange(n_users, dtype=torch.int64), n_truth)
-    order = torch.argsort(rows * (1 << 32) + (ti + 1))
-    ti_sorted = ti[order].to(torch.int32).to(dev)
-    tp_dev = tp.to(dev)
+    tp_dev = torch.as_tensor(np.asarray(truth_indptr, dtype=np.int64)).to(dev)
+    ti = torch.as_tensor(np.asarray(truth_items, dtype=np.int64)).to(dev)
+    n_truth = (tp_dev[1:] - tp_dev[:-1])
+    # sort every truth row ascending (row id is the major key), on the device
+    rows = torch.repeat_interleave(torch.arange(n_users, dtype=torch.int64, device=dev), n_truth)
+    ti_sorted = (torch.sort(rows * (1 << 32) + (ti + 1)).values & 0xffffffff).sub_(1).to(torch.int32)
     top = sorted(int(n) for n in N)
     top_dev = torch.tensor(top, dtype=torch.int32, device=dev)
     disc = torch.tensor([1.0 / math.log(p + 2, 2) for p in range(k)], dtype=torch.float64, device=dev)

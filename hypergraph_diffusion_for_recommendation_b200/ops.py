@@ -386,14 +386,44 @@ def tall_skinny_tn(h: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
 
 
 def rows_times_small(a1: torch.Tensor, a2: torch.Tensor | None, b: torch.Tensor, bias: torch.Tensor | None = None,
-                     relu: bool = False) -> torch.Tensor:
-    """``[relu](cat([a1, a2], 1) @ b [+ bias])`` for a small ``b`` kept in shared memory (hgr_rows_times_small_bias_f32)."""
+                     relu: bool = False, gather=None) -> torch.Tensor:
+    """``[relu](cat([a1, a2], 1) @ b [+ bias])`` for a small ``b`` kept in shared memory (hgr_rows_times_small_gather_f32);
+    ``gather`` = ``(peer pointers, row offset, multicast pointer)``: the rows are also published into every rank's gathered table."""
     n, k1 = a1.shape
     k2 = 0 if a2 is None else a2.shape[1]
     y = torch.empty((n, b.shape[1]), dtype=torch.float32, device=a1.device)
-    _lib.check(_lib.lib().hgr_rows_times_small_bias_f32(a1.data_ptr(), k1, _lib.ptr(a2), k2, b.data_ptr(), b.shape[1], n, y.data_ptr(),
-                                                        _lib.ptr(bias), 1 if relu else 0, _lib.stream_ptr()))
+    g = None if gather is None else C.byref(_lib.make_gather(*gather))
+    _lib.check(_lib.lib().hgr_rows_times_small_gather_f32(a1.data_ptr(), k1, _lib.ptr(a2), k2, b.data_ptr(), b.shape[1], n, y.data_ptr(),
+                                                          _lib.ptr(bias), 1 if relu else 0, g, _lib.stream_ptr()))
     return y
+
+
+class _AddRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, publish):
+        a, b = a.contiguous(), b.contiguous()
+
+        def run(gather):
+            out = torch.empty_like(a)
+            g = None if gather is None else C.byref(_lib.make_gather(*gather))
+            _lib.check(_lib.lib().hgr_add_rows_f32(a.data_ptr(), b.data_ptr(), a.shape[0], a.shape[1], out.data_ptr(), g, _lib.stream_ptr()))
+            return out
+
+        return publish.publish_by(a.shape[1], run) if publish is not None else run(None)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy, None
+
+
+def add_rows(a: torch.Tensor, b: torch.Tensor, publish=None) -> torch.Tensor:
+    """``a + b`` for two ``[rows, D]`` float32 CUDA tables on ``hgr_add_rows_f32``; ``publish`` (a sharded ``dist.DistGraph``): the sum
+    is also stored into every rank's gathered table by the same kernel, so the propagation that consumes it needs no exchange."""
+    if publish is not None and not (getattr(publish, "fused", False) and a.shape[0] == publish.part.n_loc):
+        publish = None
+    if not (a.is_cuda and a.dtype == b.dtype == torch.float32 and a.dim() == 2 and a.shape == b.shape and a.shape[1] % 4 == 0):
+        return a + b
+    return _AddRows.apply(a, b, publish)
 
 
 def hyperedge_supported(h: torch.Tensor, e: torch.Tensor) -> bool:
@@ -470,9 +500,13 @@ class _Linear(torch.autograd.Function):
     rows that cuBLAS runs as a few-block SIMT kernel (0.84 ms) -- on the tall-skinny reduce of csrc/hyperedge.cu.  No library GEMM."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):
+    def forward(ctx, x, weight, bias, relu, publish=None):
         x = x.contiguous()
-        y = rows_times_small(x, None, weight.t().contiguous(), None if bias is None else bias.contiguous(), relu)
+        wt, bb = weight.t().contiguous(), None if bias is None else bias.contiguous()
+        if publish is not None:  # sharded: the output rows go into every rank's gathered table from this kernel's epilogue
+            y = publish.publish_by(wt.shape[1], lambda gather: rows_times_small(x, None, wt, bb, relu, gather))
+        else:
+            y = rows_times_small(x, None, wt, bb, relu)
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.has_bias, ctx.relu = bias is not None, relu
         return y
@@ -486,10 +520,10 @@ class _Linear(torch.autograd.Function):
         dx = rows_times_small(dy, None, weight.contiguous()) if ctx.needs_input_grad[0] else None  # dy [n, out] x weight [out, in]
         dw = tall_skinny_tn(dy, x) if ctx.needs_input_grad[1] else None
         db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool = False) -> torch.Tensor:
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool = False, publish=None) -> torch.Tensor:
     """Drop-in for ``nn.Linear.forward`` (``relu=True``: followed by ``F.relu``) on ``[rows, in]`` float32 CUDA inputs:
     out in {32, 64, 128, 256}, in in {32, 64, 128} -- the widths of every Linear on the hot path (MLP / lin_in of the ED-HNN
     blocks).  Anything else raises: there is no library fallback behind it."""
@@ -498,4 +532,6 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, rel
     if not (x.dim() == 2 and x.dtype == weight.dtype == torch.float32 and weight.shape[0] in (32, 64, 128, 256)
             and weight.shape[1] in (32, 64, 128) and x.shape[1] == weight.shape[1]):
         raise ValueError("linear: need float32 x [rows, 32|64|128] and weight [32|64|128|256, in], got %s and %s" % (tuple(x.shape), tuple(weight.shape)))
-    return _Linear.apply(x, weight, bias, relu)
+    if publish is not None and not (getattr(publish, "fused", False) and x.shape[0] == publish.part.n_loc):
+        publish = None  # only a sharded graph with the fused exchange can carry the rows
+    return _Linear.apply(x, weight, bias, relu, publish)

@@ -239,6 +239,13 @@ int hgr_rows_times_small_f32(const float *A1, int32_t K1, const float *A2, int32
  * instead of cuBLAS sgemm + bias kernel + ReLU kernel.  bias may be NULL. */
 int hgr_rows_times_small_bias_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
                                   float *Y, const float *bias, int32_t relu, hgr_stream_t stream);
+/* ... whose finished rows are ALSO published into every rank's gathered table (sharded training: the Linear that feeds a
+ * propagation, model/graph/HGNN_HD3.py:600-601, carries the exchange in its epilogue).  gather may be NULL. */
+int hgr_rows_times_small_gather_f32(const float *A1, int32_t K1, const float *A2, int32_t K2, const float *B, int32_t N, int64_t n,
+                                    float *Y, const float *bias, int32_t relu, const hgr_gather_t *gather, hgr_stream_t stream);
+/* out = a + b on [n_rows, D] tables (the "+ res" that closes an encoder layer, model/graph/HGNN_HD3.py:419), the sum published
+ * the same way.  gather may be NULL. */
+int hgr_add_rows_f32(const float *a, const float *b, int64_t n_rows, int32_t D, float *out, const hgr_gather_t *gather, hgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BPR + L2 loss fused with the embedding gathers (util/loss_torch.py:5-9,17-21 called from

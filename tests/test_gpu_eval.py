@@ -303,3 +303,26 @@ def test_device_metric_sums_reproduce_the_python_sums_bit_for_bit(E):
         for d, m in zip(dcg[:, 0].cpu().numpy().tolist(), n_truth.tolist()):
             nd += d / idcg[min(m, 20)]
         assert out_n.item() == nd
+
+
+def test_popular_items_with_low_ids_do_not_overflow_the_candidate_lists(E):
+    """Ids are handed out in order of first appearance (data/ui_graph.py:43-68), so the popular items -- every user's best
+    candidates after training -- share the first tiles of the catalogue: one (sub-range, column half) list must be able to take
+    a user's whole candidate set.  40 000 items (so the catalogue is cut into many sub-ranges), the first 150 of them aligned
+    with every user: exact results, and nobody falls back to the brute-force kernel."""
+    rng = np.random.default_rng(77)
+    n_users, n_items, k = 12_000, 40_000, 20
+    common = rng.standard_normal(64).astype(np.float32)
+    ue = (0.1 * rng.standard_normal((n_users, 64)) + 0.5 * common).astype(np.float32)
+    ie = (0.1 * rng.standard_normal((n_items, 64))).astype(np.float32)
+    ie[:150] += (0.5 * common * rng.uniform(0.5, 1.5, (150, 1))).astype(np.float32)
+    tu = rng.integers(0, n_users, 100_000)
+    ti = np.minimum((rng.pareto(1.2, 100_000) * 40).astype(np.int64), n_items - 1)  # training items concentrate on low ids too
+    ptr, idx = train_csr(tu, ti, n_users)
+    users = np.arange(0, n_users, 97)
+    want_ids, want_sc = O.fullrank_topk(ue, ie, users, ptr, idx, k, mode="exact")
+    all_users = np.arange(n_users, dtype=np.int32)
+    ids, sc, stats = run(E, ue, ie, all_users, ptr, idx, k, "exact", "tensor")
+    assert np.array_equal(ids[users], want_ids) and np.array_equal(sc[users].view(np.uint32), want_sc.view(np.uint32))
+    assert stats[2] == 0, "%d users overflowed their candidate lists" % stats[2]
+    assert (ids[:, :k] < 150).mean() > 0.9  # the case really is concentrated
