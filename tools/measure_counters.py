@@ -28,6 +28,8 @@ JOBS = {
     # name: (cache key prefix, kernel regex, launches to capture, probe command)
     "spmm_c5w": ("spmm:c5w:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "1250000x250000x125000000", "--variants", "0", "--schedules", "auto", "--iters", "1"]),
     "spmm_c5w8": ("spmm:c5w:8", "spmm_rows_async", 1, ["tools/shard_probe.py", "--schedules", "auto", "--iters", "1"]),
+    "spmm_c5w4": ("spmm:c5w:4", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "4", "--schedules", "auto", "--iters", "1"]),
+    "spmm_c5w2": ("spmm:c5w:2", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "2", "--schedules", "auto", "--iters", "1"]),
     "spmm_c4": ("spmm:c4:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "52000x92000x3000000", "--variants", "0", "--schedules", "auto", "--iters", "1"]),
     "eval_c5w": ("eval:c5w:1", "eval_scores", 2, ["tools/eval_probe.py", "--shape", "c5e", "--users", "262144", "--iters", "1"]),
     "eval_c4": ("eval:c4:1", "eval_scores", 2, ["tools/eval_probe.py", "--shape", "c4", "--iters", "1"]),
@@ -60,11 +62,13 @@ def run_ncu(regex, count, metrics, cmd):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default=",".join(JOBS))
+    ap.add_argument("--merge", default=os.path.join(ROOT, "profiles", "kernel_counters.json"), help="existing cache to start from")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_counters.json"))
     args = ap.parse_args()
     out = {}
-    if os.path.exists(args.out):
-        out = json.load(open(args.out))
+    for path in (args.merge, args.out):
+        if path and os.path.exists(path):
+            out.update(json.load(open(path)))
     for name in args.what.split(","):
         prefix, regex, count, cmd = JOBS[name]
         launches = run_ncu(regex, count, SPMM_METRICS if prefix.startswith("spmm") else EVAL_METRICS, cmd)
