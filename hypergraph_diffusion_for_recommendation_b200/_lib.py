@@ -23,6 +23,7 @@ class CsrDesc(C.Structure):
         ("chunk_nnz", C.c_int32), ("n_heavy_rows", C.c_int32), ("n_chunks", C.c_int64),
         ("heavy_rows", C.c_void_p), ("heavy_chunk_ptr", C.c_void_p), ("chunk_owner", C.c_void_p),
         ("work_order", C.c_void_p), ("n_work", C.c_int64),
+        ("chunk_start", C.c_void_p),
     ]
 
 
@@ -88,6 +89,8 @@ SIGNATURES = {
     "hgr_bpr_l2_fwd_f32": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, _VP, _VP, _I64, _F32, _F32, _VP, _VP, _SZ, _VP, _VP]),
     "hgr_rank_metrics": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "hgr_drop_edges_f32": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _I64, _F32, C.c_uint64, _VP, _VP, _VP, _I32, _VP, _VP]),
+    "hgr_window_split_count": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP]),
+    "hgr_window_split_fill": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP]),
     "hgr_rank_metric_sums": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "hgr_bpr_sample": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP, _VP, _I32, C.c_uint64, C.c_uint64, _VP, _VP, _VP, _VP, _VP]),
     "hgr_ssl_workspace_bytes": (_SZ, [_I64, _I32]),

@@ -26,6 +26,7 @@ namespace hgr {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 8;  // partial-row reduce kernel
+constexpr int kGroupReduceMax = 64;  // a split row with at most this many chunks is summed by one row group
 
 // Tuning variant (unroll depth of the gather batch x resident blocks per SM); see hgr_set_spmm_variant.
 static int g_variant = 0;  // 0 = cp.async ring of 2 x 4 rows per group, 5 blocks/SM
@@ -269,9 +270,14 @@ __device__ __forceinline__ WorkItem resolve_work(const hgr_csr_t &A, int g, int 
     if (chunk >= 0) {
         const int h = A.chunk_owner[chunk];
         const int r = A.heavy_rows[h];
-        w.s = A.indptr[r] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
         const int64_t row_end = A.indptr[r + 1];
-        w.e = w.s + A.chunk_nnz < row_end ? w.s + A.chunk_nnz : row_end;
+        if (A.chunk_start) {  // explicit boundaries (window-aligned plan)
+            w.s = A.chunk_start[chunk];
+            w.e = chunk + 1 < A.heavy_chunk_ptr[h + 1] ? A.chunk_start[chunk + 1] : row_end;
+        } else {
+            w.s = A.indptr[r] + (chunk - A.heavy_chunk_ptr[h]) * (int64_t)A.chunk_nnz;
+            w.e = w.s + A.chunk_nnz < row_end ? w.s + A.chunk_nnz : row_end;
+        }
         w.target = chunk;
         w.kind = 1;
         return w;
@@ -317,9 +323,9 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_rows_async_kernel(hgr_csr
 }
 
 // Sums the partial rows of the split rows and runs the epilogue.  A block takes GPB consecutive split rows.  Most of them
-// have a handful of chunks (a power-law tail cut at chunk_nnz): ONE group adds those in chunk order.  A row with more than
-// GPB chunks is then reduced by the whole block: group g adds chunks g, g + GPB, ... in order, group 0 adds the GPB group
-// sums in group order (for <= GPB chunks the two orders are the same chain, so the split point never changes a bit).
+// have a handful of chunks (a power-law tail cut at chunk_nnz, or one chunk per table window the row crosses): ONE group adds
+// those in chunk order, up to kGroupReduceMax chunks.  A row with more chunks is then reduced by the whole block: group g
+// adds chunks g, g + GPB, ... in order, group 0 adds the GPB group sums in group order.
 // A fixed order either way: deterministic.  The first version launched one block per split row - 22 000 blocks of which
 // all but a few hundred used 1/16 of their threads (0.14 ms per propagation).
 template <int LPR>
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A
         const int h = h0 + g;
         if (h < h_end) {
             const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
-            if (c1 - c0 <= GPB) {
+            if (c1 - c0 <= kGroupReduceMax) {
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int64_t c = c0; c < c1; c += 4) {  // four loads in flight, added in chunk order
                     float4 p[4];
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(kThreads) spmm_heavy_reduce_kernel(hgr_csr_t A
     }
     for (int h = h0; h < h_end; ++h) {  // block-uniform loop: the rows with more chunks than groups
         const int64_t c0 = A.heavy_chunk_ptr[h], c1 = A.heavy_chunk_ptr[h + 1];
-        if (c1 - c0 <= GPB) continue;
+        if (c1 - c0 <= kGroupReduceMax) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t c = c0 + g; c < c1; c += (int64_t)GPB * kUnroll) {
             float4 p[kUnroll];
@@ -402,6 +408,8 @@ static int check_csr(const hgr_csr_t *A, const char *name) {
                 (long long)A->n_work);
     if (A->work_order)
         HGR_REQUIRE(A->n_work <= (int64_t)A->n_rows + A->n_chunks, "%s: work list longer than rows + chunks", name);
+    if (A->chunk_start)
+        HGR_REQUIRE(A->n_heavy_rows > 0 && A->work_order, "%s: explicit chunk boundaries need a split plan and a work list", name);
     return HGR_OK;
 }
 

@@ -418,7 +418,7 @@ class Interaction(Data):
         else:
             graph._scale(adj_mat.indptr, adj_mat.indices, vals, adj_mat.shape[0], graph._degree_scale(deg, -1.0), None)
         return graph.DeviceCSR(adj_mat.indptr, adj_mat.indices, vals, adj_mat.shape, symmetric=adj_mat.symmetric,
-                               chunk_nnz=adj_mat.chunk_nnz)
+                               chunk_nnz=adj_mat.chunk_nnz, split=adj_mat.split)
 
     def convert_to_laplacian_mat(self, adj_mat):
         """data/ui_graph.py:86-93: the normalised ``(U+I)^2`` adjacency of a (perturbed) ``[U, I]`` interaction matrix, whose
@@ -436,7 +436,7 @@ class Interaction(Data):
         # user rows keep the order of adj_mat's rows; item rows list the same entries sorted by (item, user)
         vals = torch.cat([v, v[torch.sort(c, stable=True).indices]])
         return self.normalize_graph_mat(graph.DeviceCSR(pattern.indptr, pattern.indices, vals, pattern.shape, symmetric=True,
-                                                        chunk_nnz=pattern.chunk_nnz))
+                                                        chunk_nnz=pattern.chunk_nnz, split=pattern.split))
 
     # ---- accessors (data/ui_graph.py:114-178) -----------------------------------------------------------------------
     def get_user_id(self, u):

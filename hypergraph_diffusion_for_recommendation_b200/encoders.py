@@ -230,7 +230,7 @@ class SpAdjDropEdge(nn.Module):
         counts = torch.bincount(rows[mask], minlength=adj.shape[0])
         indptr = torch.zeros(adj.shape[0] + 1, dtype=torch.int64, device=adj.device)
         torch.cumsum(counts, 0, out=indptr[1:])
-        return DeviceCSR(indptr, adj.indices[mask], adj.values[mask] / keep, adj.shape, chunk_nnz=adj.chunk_nnz)
+        return DeviceCSR(indptr, adj.indices[mask], adj.values[mask] / keep, adj.shape, chunk_nnz=adj.chunk_nnz, split=adj.split)
 
 
 class MLP(nn.Module):

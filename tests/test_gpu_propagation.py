@@ -509,3 +509,39 @@ def test_drop_edges_philox_mask_is_a_consistent_transpose_pair_and_changes_with_
     y.sum().backward()
     want = np.asarray(at @ np.ones((n, 64), np.float32))                   # d/dx sum(A x) = A^T 1
     assert rel_err(x.grad, want) < RTOL
+
+
+def test_window_split_plan_device_matches_rule_and_oracle(hgr, pl_graph):
+    """The window-aligned split plan (csrc/split_plan.cu): the device walk gives the plan of the python restatement; the
+    propagation with it is reproducible, independent of the schedule, within 1e-5 of the oracle and bit-exact on whole rows."""
+    from hypergraph_diffusion_for_recommendation_b200 import graph
+
+    n = pl_graph["n_users"] + pl_graph["n_items"]
+    indptr, indices, vals = pl_graph["csr"]
+    shift, min_seg, max_seg = 4, 3, 12  # 16-row windows of the 150-row table
+    for span in (3, 0):
+        want = graph.window_split_plan_host(indptr, indices, shift, min_seg, max_seg, span)
+        got = graph.window_split_plan(cuda(indptr.astype(np.int64)), cuda(indices.astype(np.int32)), shift, min_seg, max_seg, span)
+        for w, g in zip(want, got):
+            assert np.array_equal(w, g.cpu().numpy())
+    assert want[0].size > 10 and want[3].size > 2 * want[0].size
+    a = hgr.graph.DeviceCSR.from_host(indptr, indices, vals, (n, n), symmetric=True, chunk_nnz=max_seg, split="window:%d:%d:0" % (shift, min_seg))
+    assert a.split.startswith("window") and a.desc.chunk_start
+    assert (int(a.desc.n_heavy_rows), int(a.desc.n_chunks)) == (want[0].size, want[3].size)
+    x = np.random.default_rng(3).standard_normal((n, 64)).astype(np.float32)
+    ref = O.spmm(indptr, indices, vals, x)
+    outs = []
+    for sched in ("binned", "windowed:16", "interleaved", "stored"):
+        a.set_schedule(sched)
+        outs.append(hgr.ops.spmm_raw(a, cuda(x)))
+    for y in outs[1:]:
+        assert torch.equal(y, outs[0])
+    assert rel_err(outs[0], ref) < RTOL
+    whole = np.ones(n, dtype=bool)
+    whole[want[0]] = False
+    assert np.array_equal(bits(outs[0])[whole], bits(ref)[whole])
+    # backward goes through the same plan (symmetric matrix): gradient of sum(Y * G) is A^T G
+    g = np.random.default_rng(4).standard_normal((n, 64)).astype(np.float32)
+    xt = cuda(x).requires_grad_(True)
+    (hgr.ops.spmm(a, xt) * cuda(g)).sum().backward()
+    assert rel_err(xt.grad, O.spmm(indptr, indices, vals, g)) < RTOL

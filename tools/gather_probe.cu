@@ -9,6 +9,7 @@
 //              peak, a large one the DRAM read peak.
 //
 // Built by tools/gather_probe.py with nvcc -gencode arch=compute_100a,code=sm_100a into tools/libgather_probe.so.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -120,6 +121,89 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_reg_kernel(const int *_
     out[group * LPR + gl] = acc;
 }
 
+// TMA tile::gather4 (sm_100): ONE instruction from one lane fetches the 4 table rows whose indices it names (1 KB) into
+// shared memory and signals an mbarrier; no per-lane LDGSTS.  Ring of STAGES x 4 rows per 16-lane group, one mbarrier per stage.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (!done && spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, int c0, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+                 : "memory");
+}
+
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) gather_tma_kernel(const int *__restrict__ idx, int64_t nnz, const __grid_constant__ CUtensorMap tm,
+                                                                float4 *__restrict__ out, int per_group) {
+    extern __shared__ __align__(1024) uint8_t tma_smem[];  // [groups][STAGES][4 rows][256 B], then the mbarriers
+    constexpr int GPB = kThreads / LPR;
+    const int g = threadIdx.x / LPR, gl = threadIdx.x % LPR;
+    const unsigned gmask = 0xffffu << ((threadIdx.x % 32) / LPR * LPR);
+    uint8_t *ring = tma_smem + (size_t)g * STAGES * 1024;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tma_smem + (size_t)GPB * STAGES * 1024) + g * STAGES;
+    if (gl == 0)
+        for (int s = 0; s < STAGES; ++s) mbar_init(smem_addr(bars + s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int64_t group = (int64_t)blockIdx.x * GPB + g;
+    const int64_t s0 = group * per_group;
+    int64_t e = s0 + per_group;
+    if (e > nnz) e = nnz;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s0 < e) {
+        const int n_sub = (int)((e - s0) / 4);  // per_group is a multiple of 16: whole quads (the tail of the stream is dropped)
+        int c_iss = (s0 + gl < e) ? ld_stream_i32(idx + s0 + gl) : 0;
+        int c_pre = (s0 + LPR + gl < e) ? ld_stream_i32(idx + s0 + LPR + gl) : 0;
+#pragma unroll 1
+        for (int sub = 0; sub < n_sub + STAGES - 1; ++sub) {
+            if (sub < n_sub) {
+                const int first = (sub * 4) % LPR;
+                const int r0 = __shfl_sync(gmask, c_iss, first, LPR), r1 = __shfl_sync(gmask, c_iss, first + 1, LPR);
+                const int r2 = __shfl_sync(gmask, c_iss, first + 2, LPR), r3 = __shfl_sync(gmask, c_iss, first + 3, LPR);
+                if (gl == 0) {
+                    const uint32_t bar = smem_addr(bars + sub % STAGES);
+                    mbar_expect(bar, 1024);
+                    tma_gather4(smem_addr(ring + (sub % STAGES) * 1024), &tm, 0, r0, r1, r2, r3, bar);
+                }
+                if (first + 4 == LPR) {
+                    c_iss = c_pre;
+                    const int64_t p = s0 + ((int64_t)sub * 4 / LPR + 2) * LPR + gl;
+                    c_pre = (p < e) ? ld_stream_i32(idx + p) : 0;
+                }
+            }
+            const int cons = sub - (STAGES - 1);
+            if (cons >= 0) {
+                mbar_wait(smem_addr(bars + cons % STAGES), (cons / STAGES) & 1);
+                const float4 *rows = reinterpret_cast<const float4 *>(ring + (cons % STAGES) * 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 x = rows[k * LPR + gl];
+                    acc.x += x.x;
+                    acc.y += x.y;
+                    acc.z += x.z;
+                    acc.w += x.w;
+                }
+                __syncwarp(gmask);  // every lane of the group has read the stage before lane 0 re-arms it
+            }
+        }
+    }
+    out[group * LPR + gl] = acc;
+}
+
 __global__ void __launch_bounds__(kThreads) stream_kernel(const float4 *__restrict__ buf, int64_t n4, int repeat, float4 *__restrict__ out) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -188,6 +272,41 @@ int gp_gather(const int *idx, int64_t nnz, const float *X, float *out, int varia
         case 12: return launch_reg<16, 2>(idx, nnz, X, out, per_group, st);
         default: return -1;
     }
+}
+
+// TMA gather4 variant: table [n_rows, 64] fp32.  Returns -3 when the driver refuses the tensor map.
+int gp_gather_tma(const int *idx, int64_t nnz, const float *X, int64_t n_rows, float *out, int variant, int per_group, int box_rows, cudaStream_t st) {
+    if (per_group <= 0 || per_group % LPR) return -1;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -3;
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {64, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((encode_fn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -3;
+    const int64_t groups = (nnz + per_group - 1) / per_group;
+    const int64_t grid = (groups + kThreads / LPR - 1) / (kThreads / LPR);
+#define GP_TMA(STG, MB)                                                                                                        \
+    do {                                                                                                                       \
+        const size_t smem = (size_t)(kThreads / LPR) * STG * 1024 + (size_t)(kThreads / LPR) * STG * 8;                         \
+        if (cudaFuncSetAttribute(gather_tma_kernel<STG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; \
+        gather_tma_kernel<STG, MB><<<(unsigned)grid, kThreads, smem, st>>>(idx, nnz, tm, (float4 *)out, per_group);             \
+    } while (0)
+    switch (variant) {
+        case 0: GP_TMA(2, 5); break;
+        case 1: GP_TMA(3, 4); break;
+        case 2: GP_TMA(4, 3); break;
+        case 3: GP_TMA(2, 6); break;
+        default: return -1;
+    }
+#undef GP_TMA
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int gp_stream(const float *buf, int64_t n_floats, int repeat, int blocks, float *out, cudaStream_t st) {

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,10,11,12")
     ap.add_argument("--per-group", default="256,1024")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--tma", default="", help="comma list of TMA gather4 variants (0: 2 stages x 5 blocks, 1: 3x4, 2: 4x3, 3: 2x6)")
+    ap.add_argument("--skip-streams", action="store_true")
     args = ap.parse_args()
     build()
     if args.build_only:
@@ -52,6 +54,7 @@ def main():
 
     lib = C.CDLL(SO)
     lib.gp_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.gp_gather_tma.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gp_stream.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     dev = torch.device("cuda:0")
     st = torch.cuda.current_stream().cuda_stream
@@ -74,7 +77,7 @@ def main():
 
     sink = torch.empty(64, device=dev)
     print("== coalesced streaming reads (ld.global.cg.v4, 148 x 8 blocks of 256 threads)")
-    for mb, rep in ((32, 64), (64, 32), (96, 24), (4096, 1)):
+    for mb, rep in (() if args.skip_streams else ((32, 64), (64, 32), (96, 24), (4096, 1))):
         buf = torch.empty(mb << 18, device=dev)  # mb MiB of floats
         buf.normal_()
         ms = timeit(lambda: lib.gp_stream(buf.data_ptr(), buf.numel(), rep, 148 * 8, sink.data_ptr(), st), do_flush=mb > 126)
@@ -109,6 +112,29 @@ def main():
                     torch.cuda.synchronize()
                     ms = timeit(lambda: lib.gp_gather(ids.data_ptr(), nnz, tab.data_ptr(), out.data_ptr(), v, pg, st))
                     print("     %-46s per_group %4d: %.3f ms -> %.2f TB/s, %.1f Gnnz/s" % (RING[v], pg, ms, nnz * 256 / ms / 1e9, nnz / ms / 1e6), flush=True)
+                if args.tma:
+                    want = torch.empty_like(out)
+                    lib.gp_gather(ids.data_ptr(), nnz, tab.data_ptr(), want.data_ptr(), 0, pg, st)
+                    for v in (int(v) for v in args.tma.split(",")):
+                        for box in (1, 4):
+                            out.zero_()
+                            rc = lib.gp_gather_tma(ids.data_ptr(), nnz, tab.data_ptr(), tab.shape[0], out.data_ptr(), v, pg, box, st)
+                            try:
+                                torch.cuda.synchronize()
+                            except RuntimeError as e:
+                                print("     TMA gather4 variant %d box %d: launch died: %s" % (v, box, str(e)[:200]))
+                                raise
+                            if rc:
+                                print("     TMA gather4 variant %d box %d failed (%d)" % (v, box, rc))
+                                continue
+                            n_full = (nnz // pg) * 64
+                            same = torch.equal(out[:n_full], want[:n_full])
+                            close = torch.allclose(out[:n_full], want[:n_full], rtol=1e-4, atol=1e-4)
+                            ms = timeit(lambda: lib.gp_gather_tma(ids.data_ptr(), nnz, tab.data_ptr(), tab.shape[0], out.data_ptr(), v, pg, box, st))
+                            print("     TMA gather4 variant %d box rows %d          per_group %4d: %.3f ms -> %.2f TB/s, %.1f Gnnz/s  (bit-equal to ring: %s, close: %s)"
+                                  % (v, box, pg, ms, nnz * 256 / ms / 1e9, nnz / ms / 1e6, same, close), flush=True)
+                            if close:
+                                break
                 del out
         del adj, x, streams
 

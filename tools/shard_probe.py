@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--variants", default="0", help="hgr_set_spmm_variant values to time (include/hgr.h)")
     ap.add_argument("--schedules", default="stored,binned,windowed", help="work schedules to time (graph.work_schedule)")
+    ap.add_argument("--splits", default="fixed", help="split plans: fixed | window[:shift[:min_seg]]")
+    ap.add_argument("--chunks", default="0", help="chunk_nnz values of the split plan to time (0 = the default rule)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     U, I, E = 1_250_000 * args.world, 250_000 * args.world, 125_000_000 * args.world
@@ -41,7 +43,27 @@ def main():
     x = torch.randn(part.n_glob, 64, device=dev)
     from hypergraph_diffusion_for_recommendation_b200 import _lib
 
-    for sched, variant in ((s, int(v)) for s in args.schedules.split(",") for v in args.variants.split(",")):
+    deg = (indptr[1:] - indptr[:-1])
+    for name, dsel in (("user rows", deg[:part.up]), ("item rows", deg[part.up:])):
+        tot = int(dsel.sum())
+        line = ["%s: %d rows, %d nnz" % (name, dsel.numel(), tot)]
+        for lo, hi in ((0, 64), (64, 256), (256, 1024), (1024, 4096), (4096, 16384), (16384, 1 << 40)):
+            m = (dsel >= lo) & (dsel < hi)
+            line.append("[%d,%s): %d rows %.1f%% nnz" % (lo, hi if hi < (1 << 40) else "inf", int(m.sum()), 100.0 * int(dsel[m].sum()) / max(tot, 1)))
+        print("  " + " | ".join(line), flush=True)
+    del block
+    made = None
+    for chunk, split, sched, variant in ((int(c), sp, s, int(v)) for c in args.chunks.split(",") for sp in args.splits.split(",")
+                                         for s in args.schedules.split(",") for v in args.variants.split(",")):
+        if made != (chunk, split):
+            block = None
+            torch.cuda.empty_cache()
+            t0 = time.time()
+            block = DeviceCSR(indptr, indices, values, (part.n_loc, part.n_glob), chunk_nnz=chunk or None, split=split)
+            torch.cuda.synchronize()
+            made = (chunk, split)
+            print("split %s chunk_nnz %d: heavy rows %d, chunks %d, plan %.2f s" % (block.split, block.chunk_nnz, block.desc.n_heavy_rows,
+                                                                               block.desc.n_chunks, time.time() - t0), flush=True)
         block.set_schedule(sched)
         _lib.check(_lib.lib().hgr_set_spmm_variant(variant))
         print("schedule %s variant %d" % (sched, variant), flush=True)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--chunks", default="0")
     ap.add_argument("--variants", default="0")
     ap.add_argument("--schedules", default="stored,binned,interleaved")
+    ap.add_argument("--splits", default="fixed", help="split plans to time: fixed | window[:shift[:min_seg]] (graph.DeviceCSR)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--d", type=int, default=64)
     args = ap.parse_args()
@@ -32,20 +33,26 @@ def main():
         t0 = time.time()
         u, i = powerlaw_interactions_device(U, I, E, dev)
         torch.cuda.synchronize()
-        t1 = time.time()
-        for chunk in (int(c) for c in args.chunks.split(",")):
-            adj = norm_adj_from_pairs_torch(u, i, U, I, chunk_nnz=chunk or None)
+        from hypergraph_diffusion_for_recommendation_b200.graph import DeviceCSR
+
+        base = norm_adj_from_pairs_torch(u, i, U, I, chunk_nnz=1 << 30)
+        n, nnz = U + I, base._nnz()
+        x = torch.randn(n, args.d, device=dev)
+        y_seq = ops.spmm_raw(base, x).clone()  # every row accumulated sequentially (no split plan)
+        for chunk, split in ((int(c), sp) for c in args.chunks.split(",") for sp in args.splits.split(",")):
+            torch.cuda.synchronize()
+            t1 = time.time()
+            adj = DeviceCSR(base.indptr, base.indices, base.values, base.shape, symmetric=True, chunk_nnz=chunk or None, split=split)
             torch.cuda.synchronize()
             t2 = time.time()
-            n, nnz = U + I, adj._nnz()
-            x = torch.randn(n, args.d, device=dev)
             deg = adj.indptr[1:] - adj.indptr[:-1]
-            print("shape %s nnz %d gen %.1fs build %.1fs chunk %d heavy_rows %d chunks %d maxdeg %d" % (
-                shape, nnz, t1 - t0, t2 - t1, adj.chunk_nnz, adj.desc.n_heavy_rows, adj.desc.n_chunks, int(deg.max())), flush=True)
+            print("shape %s nnz %d plan %.2fs split %s chunk %d heavy_rows %d chunks %d maxdeg %d" % (
+                shape, nnz, t2 - t1, adj.split, adj.chunk_nnz, adj.desc.n_heavy_rows, adj.desc.n_chunks, int(deg.max())), flush=True)
             _lib.check(_lib.lib().hgr_set_spmm_variant(5))
+            adj.set_schedule("binned")
             y_ref = ops.spmm_raw(adj, x).clone()
-            adj.set_schedule("stored")
-            y_ref = ops.spmm_raw(adj, x).clone()
+            err = ((y_ref - y_seq).abs().amax(1) / y_seq.abs().amax(1).clamp(min=1e-30)).max()
+            print("  vs sequential rows: worst row-wise relative difference %.2e" % float(err), flush=True)
             for sched, variant in ((s, int(v)) for s in args.schedules.split(",") for v in args.variants.split(",")):
                 adj.set_schedule(sched)
                 _lib.check(_lib.lib().hgr_set_spmm_variant(variant))
@@ -66,7 +73,8 @@ def main():
                 b = algorithmic_bytes(n, nnz, args.d)
                 print("  %-11s variant %d | spmm median %.3f ms min %.3f ms | alg %.1f MB -> %.0f GB/s | %.1f Gnnz/s" % (
                     sched, variant, ms, min(times), b / 1e6, b / ms / 1e6, nnz / ms / 1e6), flush=True)
-            del adj, x, y
+            del adj, y
+        del base, x, y_seq
 
 
 if __name__ == "__main__":
