@@ -26,11 +26,11 @@ EVAL_METRICS = ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed
 
 JOBS = {
     # name: (cache key prefix, kernel regex, launches to capture, probe command)
-    "spmm_c5w": ("spmm:c5w:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "1250000x250000x125000000", "--variants", "0", "--schedules", "auto", "--iters", "1"]),
-    "spmm_c5w8": ("spmm:c5w:8", "spmm_rows_async", 1, ["tools/shard_probe.py", "--schedules", "auto", "--iters", "1"]),
-    "spmm_c5w4": ("spmm:c5w:4", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "4", "--schedules", "auto", "--iters", "1"]),
-    "spmm_c5w2": ("spmm:c5w:2", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "2", "--schedules", "auto", "--iters", "1"]),
-    "spmm_c4": ("spmm:c4:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "52000x92000x3000000", "--variants", "0", "--schedules", "auto", "--iters", "1"]),
+    "spmm_c5w": ("spmm:c5w:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "1250000x250000x125000000", "--variants", "0", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
+    "spmm_c5w8": ("spmm:c5w:8", "spmm_rows_async", 1, ["tools/shard_probe.py", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
+    "spmm_c5w4": ("spmm:c5w:4", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "4", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
+    "spmm_c5w2": ("spmm:c5w:2", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "2", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
+    "spmm_c4": ("spmm:c4:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "52000x92000x3000000", "--variants", "0", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
     "eval_c5w": ("eval:c5w:1", "eval_scores", 2, ["tools/eval_probe.py", "--shape", "c5e", "--users", "262144", "--iters", "1"]),
     "eval_c4": ("eval:c4:1", "eval_scores", 2, ["tools/eval_probe.py", "--shape", "c4", "--iters", "1"]),
 }

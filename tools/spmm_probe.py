@@ -38,6 +38,7 @@ def main():
         base = norm_adj_from_pairs_torch(u, i, U, I, chunk_nnz=1 << 30)
         n, nnz = U + I, base._nnz()
         x = torch.randn(n, args.d, device=dev)
+        _lib.check(_lib.lib().hgr_set_spmm_variant(5))  # register-gather kernel: keeps `ncu -k spmm_rows_async -c 1` on the timed launches
         y_seq = ops.spmm_raw(base, x).clone()  # every row accumulated sequentially (no split plan)
         for chunk, split in ((int(c), sp) for c in args.chunks.split(",") for sp in args.splits.split(",")):
             torch.cuda.synchronize()
