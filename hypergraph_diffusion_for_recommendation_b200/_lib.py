@@ -96,6 +96,9 @@ SIGNATURES = {
     "hgr_ssl_workspace_bytes": (_SZ, [_I64, _I32]),
     "hgr_ssl_loss_fwd_f32": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, _I64, _F32, _I32, _I32, _VP, _VP, _SZ, _VP, _VP]),
     "hgr_ssl_loss_bwd_f32": (C.c_int, [_I64, _I64, _I32, _VP, _I64, _F32, _I32, _VP, _SZ, _VP, _VP, _VP, _VP]),
+    "hgr_bpr_l2_fwd_owned_f32": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, _I64, _I64, _I64, _VP, _VP, _SZ, _VP, _VP]),
+    "hgr_bpr_l2_finish_f32": (C.c_int, [_VP, _I64, _F32, _F32, _VP, _VP, _VP]),
+    "hgr_bpr_l2_bwd_owned_f32": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, _I64, _F32, _F32, _VP, _VP, _I64, _I64, _VP, _VP]),
     "hgr_bpr_l2_bwd_window_f32": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, _I64, _F32, _F32, _VP, _VP, _I64, _I64, _VP, _VP]),
     "hgr_fullrank_topk_workspace_bytes": (_SZ, [_I64, _I64, _I32, _I32, _I32]),
     "hgr_fullrank_topk_f32": (C.c_int, [_VP, _I64, _VP, _I64, _I32, _VP, _I64, _VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -23,16 +23,21 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_fwd_kernel(const float4 *
                                                                   const int64_t *__restrict__ u, const int64_t *__restrict__ p,
                                                                   const int64_t *__restrict__ n, int64_t batch, int64_t n_users,
                                                                   int64_t n_items, float *__restrict__ saved_x,
-                                                                  double *__restrict__ partials, int32_t *__restrict__ bad) {
+                                                                  double *__restrict__ partials, int32_t *__restrict__ bad,
+                                                                  int64_t own_lo, int64_t own_hi) {
+    // [own_lo, own_hi): only triples whose user row lies in the window are evaluated (owner-sharded training: each rank sums
+    // the triples of its own users); saved_x == NULL there.  The default window is everything.
     constexpr int GPB = kLossThreads / LPR;
     const int gl = threadIdx.x % LPR, g = threadIdx.x / LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
     double loss = 0.0, su = 0.0, sp = 0.0, sn = 0.0;
     for (int64_t b = (int64_t)blockIdx.x * GPB + g; b < batch; b += (int64_t)gridDim.x * GPB) {
-        const int64_t iu = u[b], ip = p[b], in = n[b];
+        const int64_t iu = u[b];
+        if (iu >= 0 && iu < n_users && (iu < own_lo || iu >= own_hi)) continue;  // another rank's user
+        const int64_t ip = p[b], in = n[b];
         if (iu < 0 || iu >= n_users || ip < 0 || ip >= n_items || in < 0 || in >= n_items) {
             if (gl == 0) atomicAdd(bad, 1);
-            if (gl == 0) saved_x[b] = 0.f;
+            if (gl == 0 && saved_x) saved_x[b] = 0.f;
             continue;
         }
         const float4 a = __ldg(user_tab + iu * LPR + gl);
@@ -45,7 +50,7 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_fwd_kernel(const float4 *
         const float nn = group_sum<LPR>((r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w), gmask);
         if (gl == 0) {
             const float x = pos - neg;
-            saved_x[b] = x;
+            if (saved_x) saved_x[b] = x;
             const float s = 1.0f / (1.0f + expf(-x));
             loss += (double)(-logf(10e-6f + s));
             su += (double)nu;
@@ -66,10 +71,25 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_fwd_kernel(const float4 *
     }
 }
 
-// out[0] = rec loss, out[1] = reg loss; norms[0..2] = ||U_B||, ||P_B||, ||N_B|| (saved for backward)
+__device__ __forceinline__ void bpr_l2_final(const double *t, int64_t batch, float reg, float batch_size_div, float *out, float *norms) {
+    const float nu = (float)sqrt(t[1]), np_ = (float)sqrt(t[2]), nn = (float)sqrt(t[3]);
+    out[0] = batch > 0 ? (float)(t[0] / (double)batch) : 0.f;
+    out[1] = (nu + np_ + nn) * reg / batch_size_div;
+    norms[0] = nu;
+    norms[1] = np_;
+    norms[2] = nn;
+}
+
+__global__ void bpr_l2_final_kernel(const double *__restrict__ sums, int64_t batch, float reg, float batch_size_div, float *__restrict__ out,
+                                    float *__restrict__ norms) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) bpr_l2_final(sums, batch, reg, batch_size_div, out, norms);
+}
+
+// out[0] = rec loss, out[1] = reg loss; norms[0..2] = ||U_B||, ||P_B||, ||N_B|| (saved for backward).  With `sums` the four
+// totals are written there instead (owner-sharded form: the caller adds them over the ranks first).
 __global__ void __launch_bounds__(256) bpr_l2_finish_kernel(const double *__restrict__ partials, int n_blocks, int64_t batch, float reg,
                                                             float batch_size_div, float *__restrict__ out,
-                                                            float *__restrict__ norms) {
+                                                            float *__restrict__ norms, double *__restrict__ sums) {
     // thread t adds blocks t, t + 256, ... in order, then a fixed tree: deterministic
     __shared__ double sh[4][256];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -84,12 +104,11 @@ __global__ void __launch_bounds__(256) bpr_l2_finish_kernel(const double *__rest
     }
     if (threadIdx.x != 0) return;
     const double t[4] = {sh[0][0], sh[1][0], sh[2][0], sh[3][0]};
-    const float nu = (float)sqrt(t[1]), np_ = (float)sqrt(t[2]), nn = (float)sqrt(t[3]);
-    out[0] = batch > 0 ? (float)(t[0] / (double)batch) : 0.f;
-    out[1] = (nu + np_ + nn) * reg / batch_size_div;
-    norms[0] = nu;
-    norms[1] = np_;
-    norms[2] = nn;
+    if (sums) {
+        for (int k = 0; k < 4; ++k) sums[k] = t[k];
+        return;
+    }
+    bpr_l2_final(t, batch, reg, batch_size_div, out, norms);
 }
 
 __device__ __forceinline__ void red_add_f4(float *addr, float4 v) {
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_bwd_kernel(const float4 *
                                                                   const float *__restrict__ norms, const float *__restrict__ grad_out,
                                                                   float reg, float batch_size_div, float *__restrict__ d_user,
                                                                   float *__restrict__ d_item, int64_t row_lo, int64_t row_hi) {
+    // saved_x == NULL: x is recomputed from the rows (owner-sharded form: the forward of this rank only saw its own users).
     // [row_lo, row_hi): only gradient rows inside the window are produced, at d[row - row_lo] (sharded training: a rank
     // owns a window of the gathered table); the default window is the whole table.
     constexpr int GPB = kLossThreads / LPR;
@@ -126,7 +146,15 @@ __global__ void __launch_bounds__(kLossThreads) bpr_l2_bwd_kernel(const float4 *
         const float4 a = __ldg(user_tab + iu * LPR + gl);
         const float4 q = __ldg(item_tab + ip * LPR + gl);
         const float4 r = __ldg(item_tab + in * LPR + gl);
-        const float x = saved_x[b];
+        float x;
+        if (saved_x) {
+            x = saved_x[b];
+        } else {
+            const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
+            const float pos = group_sum<LPR>((a.x * q.x + a.y * q.y) + (a.z * q.z + a.w * q.w), gmask);
+            const float neg = group_sum<LPR>((a.x * r.x + a.y * r.y) + (a.z * r.z + a.w * r.w), gmask);
+            x = pos - neg;
+        }
         const float s = 1.0f / (1.0f + expf(-x));
         const float gx = -(s * (1.0f - s)) / (10e-6f + s) * inv_b;  // d loss / d x
         float4 du, dp, dn;
@@ -156,13 +184,15 @@ size_t hgr_bpr_l2_workspace_bytes(int64_t batch) {
     return s + (size_t)hgr::kLossMaxBlocks * 4 * sizeof(double) + 16;
 }
 
-int hgr_bpr_l2_fwd_f32(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
-                       const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div,
-                       float *out, void *saved, size_t saved_bytes, int32_t *bad_index_count, hgr_stream_t stream) {
+static int bpr_fwd_impl(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
+                        const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div,
+                        float *out, void *saved, size_t saved_bytes, int32_t *bad_index_count, int64_t own_lo, int64_t own_hi,
+                        double *sums, hgr_stream_t stream) {
     using namespace hgr;
+    HGR_REQUIRE(sums || out, "NULL argument");
     HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
     HGR_REQUIRE(batch >= 0 && n_users >= 0 && n_items >= 0, "negative size");
-    HGR_REQUIRE(user_tab && item_tab && out && saved && bad_index_count, "NULL argument");
+    HGR_REQUIRE(user_tab && item_tab && saved && bad_index_count, "NULL argument");
     HGR_REQUIRE(batch == 0 || (u && p && n), "NULL index array");
     HGR_REQUIRE(aligned16(user_tab) && aligned16(item_tab) && aligned16(saved), "tables and workspace must be 16-byte aligned");
     HGR_REQUIRE(batch_size_div > 0.f, "batch_size_div must be positive");
@@ -171,35 +201,64 @@ int hgr_bpr_l2_fwd_f32(const float *user_tab, const float *item_tab, int64_t n_u
     float *saved_x = reinterpret_cast<float *>(saved);
     float *norms = saved_x + batch;
     double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(saved) + (((size_t)(batch + 4) * 4 + 15) & ~(size_t)15));
+    if (sums) saved_x = nullptr;  // owner-sharded: the backward recomputes x
     cudaStream_t st = (cudaStream_t)stream;
     const float4 *ut = reinterpret_cast<const float4 *>(user_tab), *it = reinterpret_cast<const float4 *>(item_tab);
     int blocks;
     switch (D) {
         case 32: blocks = loss_blocks(batch, kLossThreads / 8);
-            bpr_l2_fwd_kernel<8><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count); break;
+            bpr_l2_fwd_kernel<8><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count, own_lo, own_hi); break;
         case 64: blocks = loss_blocks(batch, kLossThreads / 16);
-            bpr_l2_fwd_kernel<16><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count); break;
+            bpr_l2_fwd_kernel<16><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count, own_lo, own_hi); break;
         default: blocks = loss_blocks(batch, kLossThreads / 32);
-            bpr_l2_fwd_kernel<32><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count); break;
+            bpr_l2_fwd_kernel<32><<<blocks, kLossThreads, 0, st>>>(ut, it, u, p, n, batch, n_users, n_items, saved_x, partials, bad_index_count, own_lo, own_hi); break;
     }
     HGR_LAUNCH_OK("bpr_l2_fwd_kernel");
-    bpr_l2_finish_kernel<<<1, 256, 0, st>>>(partials, blocks, batch, reg, batch_size_div, out, norms);
+    bpr_l2_finish_kernel<<<1, 256, 0, st>>>(partials, blocks, batch, reg, batch_size_div, out, norms, sums);
     HGR_LAUNCH_OK("bpr_l2_finish_kernel");
+    return HGR_OK;
+}
+
+int hgr_bpr_l2_fwd_f32(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D,
+                       const int64_t *u, const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div,
+                       float *out, void *saved, size_t saved_bytes, int32_t *bad_index_count, hgr_stream_t stream) {
+    HGR_REQUIRE(out, "NULL argument");
+    return bpr_fwd_impl(user_tab, item_tab, n_users, n_items, D, u, p, n, batch, reg, batch_size_div, out, saved, saved_bytes,
+                        bad_index_count, 0, n_users, nullptr, stream);
+}
+
+int hgr_bpr_l2_fwd_owned_f32(const float *table, int64_t n_rows, int32_t D, const int64_t *u, const int64_t *p, const int64_t *n,
+                             int64_t batch, int64_t own_lo, int64_t own_hi, double *sums, void *saved, size_t saved_bytes,
+                             int32_t *bad_index_count, hgr_stream_t stream) {
+    HGR_REQUIRE(sums, "NULL argument");
+    HGR_REQUIRE(own_lo >= 0 && own_lo <= own_hi && own_hi <= n_rows, "window [%lld, %lld) outside the table", (long long)own_lo,
+                (long long)own_hi);
+    return bpr_fwd_impl(table, table, n_rows, n_rows, D, u, p, n, batch, 0.f, 1.f, nullptr, saved, saved_bytes, bad_index_count, own_lo,
+                        own_hi, sums, stream);
+}
+
+int hgr_bpr_l2_finish_f32(const double *sums, int64_t batch, float reg, float batch_size_div, float *out, float *norms,
+                          hgr_stream_t stream) {
+    using namespace hgr;
+    HGR_REQUIRE(sums && out && norms, "NULL argument");
+    HGR_REQUIRE(batch >= 0 && batch_size_div > 0.f, "batch must be >= 0 and batch_size_div positive");
+    bpr_l2_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, batch, reg, batch_size_div, out, norms);
+    HGR_LAUNCH_OK("bpr_l2_final_kernel");
     return HGR_OK;
 }
 
 static int bpr_bwd_impl(const float *user_tab, const float *item_tab, int64_t n_users, int64_t n_items, int32_t D, const int64_t *u,
                         const int64_t *p, const int64_t *n, int64_t batch, float reg, float batch_size_div, const void *saved,
                         const float *grad_out, float *d_user_tab, float *d_item_tab, int64_t row_lo, int64_t row_hi,
-                        hgr_stream_t stream) {
+                        hgr_stream_t stream, const float *global_norms = nullptr) {
     using namespace hgr;
     HGR_REQUIRE(D == 32 || D == 64 || D == 128, "D = %d unsupported (32, 64 or 128)", D);
     HGR_REQUIRE(batch >= 0, "negative batch");
     if (batch == 0) return HGR_OK;
-    HGR_REQUIRE(user_tab && item_tab && u && p && n && saved && grad_out && d_user_tab && d_item_tab, "NULL argument");
+    HGR_REQUIRE(user_tab && item_tab && u && p && n && (saved || global_norms) && grad_out && d_user_tab && d_item_tab, "NULL argument");
     HGR_REQUIRE(aligned16(user_tab) && aligned16(item_tab) && aligned16(d_user_tab) && aligned16(d_item_tab), "tables must be 16-byte aligned");
-    const float *saved_x = reinterpret_cast<const float *>(saved);
-    const float *norms = saved_x + batch;
+    const float *saved_x = global_norms ? nullptr : reinterpret_cast<const float *>(saved);
+    const float *norms = global_norms ? global_norms : saved_x + batch;
     cudaStream_t st = (cudaStream_t)stream;
     const float4 *ut = reinterpret_cast<const float4 *>(user_tab), *it = reinterpret_cast<const float4 *>(item_tab);
     switch (D) {
@@ -226,6 +285,16 @@ int hgr_bpr_l2_bwd_window_f32(const float *table, int64_t n_rows, int32_t D, con
                 (long long)row_hi);
     return bpr_bwd_impl(table, table, n_rows, n_rows, D, u, p, n, batch, reg, batch_size_div, saved, grad_out, d_rows, d_rows, row_lo,
                         row_hi, stream);
+}
+
+int hgr_bpr_l2_bwd_owned_f32(const float *table, int64_t n_rows, int32_t D, const int64_t *u, const int64_t *p, const int64_t *n,
+                             int64_t batch, float reg, float batch_size_div, const float *norms, const float *grad_out,
+                             int64_t row_lo, int64_t row_hi, float *d_rows, hgr_stream_t stream) {
+    HGR_REQUIRE(norms, "NULL argument");
+    HGR_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= n_rows, "window [%lld, %lld) outside the table", (long long)row_lo,
+                (long long)row_hi);
+    return bpr_bwd_impl(table, table, n_rows, n_rows, D, u, p, n, batch, reg, batch_size_div, nullptr, grad_out, d_rows, d_rows, row_lo,
+                        row_hi, stream, norms);
 }
 
 }  // extern "C"

@@ -98,9 +98,57 @@ class _BprL2Sharded(torch.autograd.Function):
         return d, None, None, None, None, None, None, None
 
 
-def bpr_l2_sharded(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size):
-    """``(rec_loss, reg_loss)`` for sharded training; ``user_idx / pos_idx / neg_idx`` index the gathered table."""
-    out = _BprL2Sharded.apply(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size)
+class _BprL2Owned(torch.autograd.Function):
+    """The same loss with the forward sharded by OWNER: a rank evaluates the triples whose user row it
+    owns (hgr_bpr_l2_fwd_owned_f32: 1/world of the gathers), the four batch sums are added over the ranks with ONE all_reduce of
+    32 bytes (``reduce_sums``), hgr_bpr_l2_finish_f32 turns the totals into the two losses -- identical on every rank -- and the
+    backward (hgr_bpr_l2_bwd_owned_f32) produces this rank's gradient rows from every triple that touches one of them,
+    recomputing ``x`` from the rows it loads anyway.  Nothing crosses ranks but the 32 bytes."""
+
+    @staticmethod
+    def forward(ctx, own, gather, row_lo, u, p, n, reg, batch_size, reduce_sums):
+        full = gather(own).contiguous()
+        dev = full.device
+        u, p, n = _idx(u, dev), _idx(p, dev), _idx(n, dev)
+        batch = int(u.numel())
+        lib = _lib.lib()
+        n_own = int(own.shape[0])
+        scratch = torch.empty(int(lib.hgr_bpr_l2_workspace_bytes(batch)), dtype=torch.uint8, device=dev)
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        norms = torch.empty(4, dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.hgr_bpr_l2_fwd_owned_f32(full.data_ptr(), full.shape[0], full.shape[1], u.data_ptr(), p.data_ptr(), n.data_ptr(),
+                                                batch, int(row_lo), int(row_lo) + n_own, sums.data_ptr(), scratch.data_ptr(),
+                                                scratch.numel(), bad.data_ptr(), _lib.stream_ptr()))
+        reduce_sums(sums)
+        _lib.check(lib.hgr_bpr_l2_finish_f32(sums.data_ptr(), batch, float(reg), float(batch_size), out.data_ptr(), norms.data_ptr(),
+                                             _lib.stream_ptr()))
+        _raise_on_bad_index(bad, "bpr_l2_sharded (ids must index the gathered table: Partition.perm_user / perm_item)")
+        ctx.save_for_backward(full, u, p, n, norms)
+        ctx.meta = (int(row_lo), n_own, float(reg), float(batch_size))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        full, u, p, n, norms = ctx.saved_tensors
+        row_lo, n_own, reg, batch_size = ctx.meta
+        d = torch.zeros((n_own, full.shape[1]), dtype=torch.float32, device=full.device)
+        grad = grad.contiguous().to(torch.float32)
+        _lib.check(_lib.lib().hgr_bpr_l2_bwd_owned_f32(full.data_ptr(), full.shape[0], full.shape[1], u.data_ptr(), p.data_ptr(),
+                                                       n.data_ptr(), int(u.numel()), reg, batch_size, norms.data_ptr(), grad.data_ptr(),
+                                                       row_lo, row_lo + n_own, d.data_ptr(), _lib.stream_ptr()))
+        return d, None, None, None, None, None, None, None, None
+
+
+def bpr_l2_sharded(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size, reduce_sums=None):
+    """``(rec_loss, reg_loss)`` for sharded training; ``user_idx / pos_idx / neg_idx`` index the gathered table.  With
+    ``reduce_sums`` (a callable that adds a 4-element float64 tensor over the ranks in place) the forward is sharded by owner
+    (``_BprL2Owned``); without it every rank evaluates the whole batch (``_BprL2Sharded``)."""
+    if reduce_sums is not None:
+        out = _BprL2Owned.apply(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size, reduce_sums)
+    else:
+        out = _BprL2Sharded.apply(own_rows, gather, row_lo, user_idx, pos_idx, neg_idx, reg, batch_size)
     return out[0], out[1]
 
 

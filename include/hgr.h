@@ -291,6 +291,24 @@ int hgr_bpr_l2_bwd_window_f32(const float *table, int64_t n_rows, int32_t D, con
                               int64_t batch, float reg, float batch_size_div, const void *saved, const float *grad_out,
                               int64_t row_lo, int64_t row_hi, float *d_rows, hgr_stream_t stream);
 
+/* Owner-sharded forward of the same loss (dist.py, world > 1): a rank evaluates only the triples whose USER row lies in its
+ * window [own_lo, own_hi) of the gathered table and writes the four batch sums it found -- sum of -log(10e-6 + sigmoid(x)),
+ * sum |u|^2, sum |p|^2, sum |n|^2, in double -- to sums[4].  The caller adds `sums` over the ranks (one all_reduce of 32
+ * bytes) and calls hgr_bpr_l2_finish_f32, which turns the totals into out[0] = rec loss, out[1] = reg loss and
+ * norms[3] = ||U_B||, ||P_B||, ||N_B||: the same numbers on every rank, with 1/world of the gathers of the replicated form.
+ * `saved` as in hgr_bpr_l2_fwd_f32 (scratch for the per-block partial sums; nothing in it is read by the backward). */
+int hgr_bpr_l2_fwd_owned_f32(const float *table, int64_t n_rows, int32_t D, const int64_t *u, const int64_t *p, const int64_t *n,
+                             int64_t batch, int64_t own_lo, int64_t own_hi, double *sums, void *saved, size_t saved_bytes,
+                             int32_t *bad_index_count, hgr_stream_t stream);
+int hgr_bpr_l2_finish_f32(const double *sums, int64_t batch, float reg, float batch_size_div, float *out, float *norms,
+                          hgr_stream_t stream);
+/* Backward of the owner-sharded form: the gradient rows [row_lo, row_hi) this rank owns, from every triple that touches one of
+ * them (as a user, a positive or a negative); x = <u,p> - <u,n> is recomputed from the gathered table (the rows are loaded for
+ * the gradient anyway) and the norms are the global ones from hgr_bpr_l2_finish_f32.  d_rows zero-filled by the caller. */
+int hgr_bpr_l2_bwd_owned_f32(const float *table, int64_t n_rows, int32_t D, const int64_t *u, const int64_t *p, const int64_t *n,
+                             int64_t batch, float reg, float batch_size_div, const float *norms, const float *grad_out,
+                             int64_t row_lo, int64_t row_hi, float *d_rows, hgr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Full-ranking evaluation: GraphRecommender.test (base/graph_recommender.py:61-92, identical in
  * base/main_recommender.py:64-100) with predict (model/graph/LightGCN.py:99-102) and find_k_largest

@@ -105,11 +105,47 @@ def test_partition_maps_cover_every_node_once():
         assert ((pi[i0:i1] >= r * part.n_loc + part.up) & (pi[i0:i1] < (r + 1) * part.n_loc)).all()
 
 
-@pytest.mark.parametrize("world", [1, 2, 3, 8])
-def test_local_blocks_reassemble_the_global_adjacency(world):
+def test_balanced_partition_cuts_by_nonzeros():
+    """Partition.balanced: contiguous ranges, every node owned once, rank blocks with (nearly) equal nonzeros even when a few
+    items hold most interactions -- where equal-count ranges are off by tens of per cent."""
+    rng = np.random.default_rng(9)
+    n_u, n_i, world = 4000, 900, 8
+    deg_i = (rng.pareto(1.1, n_i) * 20 + 1).astype(np.int64)
+    deg_i[17] = deg_i.sum() // 12  # one item with ~8 % of everything
+    deg_u = rng.multinomial(int(deg_i.sum()), np.full(n_u, 1.0 / n_u)).astype(np.int64)
+    part = hdist.Partition.balanced(n_u, n_i, world, torch.from_numpy(deg_u), torch.from_numpy(deg_i))
+    flat = hdist.Partition(n_u, n_i, world)
+    assert not part.uniform and flat.uniform
+    pu, pi = part.perm_user(torch.arange(n_u)), part.perm_item(torch.arange(n_i))
+    allp = torch.cat([pu, pi])
+    assert allp.unique().numel() == n_u + n_i and int(allp.max()) < part.n_glob
+
+    def load(p):
+        return np.array([deg_u[slice(*p.users_of(r))].sum() + deg_i[slice(*p.items_of(r))].sum() for r in range(world)], dtype=np.float64)
+
+    for r in range(world):
+        u0, u1 = part.users_of(r)
+        i0, i1 = part.items_of(r)
+        assert u1 - u0 <= part.up and i1 - i0 <= part.ip
+        assert ((pu[u0:u1] >= r * part.n_loc) & (pu[u0:u1] < r * part.n_loc + part.up)).all()
+        assert ((pi[i0:i1] >= r * part.n_loc + part.up) & (pi[i0:i1] < (r + 1) * part.n_loc)).all()
+        assert (torch.diff(pu[u0:u1]) == 1).all() and (torch.diff(pi[i0:i1]) == 1).all()  # monotonic inside a range
+    lb, lf = load(part), load(flat)
+    assert lb.sum() == lf.sum() == deg_u.sum() + deg_i.sum()
+    assert lb.max() / lb.mean() < 1.0 + 0.6 * (lf.max() / lf.mean() - 1.0)  # the heavy item cannot be split, the rest evens out
+    with pytest.raises(ValueError):
+        hdist.Partition(n_u, n_i, world, user_bounds=(0, 5, 3) + (n_u,) * 6)
+
+
+@pytest.mark.parametrize("world,balanced", [(1, False), (2, False), (3, False), (8, False), (3, True), (8, True)])
+def test_local_blocks_reassemble_the_global_adjacency(world, balanced):
     u, i = graph()
     indptr, indices, values = O.build_norm_adj(u, i, N_USERS, N_ITEMS)
-    part = hdist.Partition(N_USERS, N_ITEMS, world)
+    if balanced:
+        part = hdist.Partition.balanced(N_USERS, N_ITEMS, world, torch.bincount(torch.from_numpy(u).long(), minlength=N_USERS),
+                                        torch.bincount(torch.from_numpy(i).long(), minlength=N_ITEMS))
+    else:
+        part = hdist.Partition(N_USERS, N_ITEMS, world)
     perm = torch.cat([part.perm_user(torch.arange(N_USERS)), part.perm_item(torch.arange(N_ITEMS))]).numpy()
     seen = 0
     for r in range(world):

@@ -51,6 +51,54 @@ def test_bpr_l2_shapes_against_oracle(L, d, batch):
     assert grad_err(tu.grad, want_du) < 2e-5 and grad_err(ti.grad, want_di) < 2e-5
 
 
+@pytest.mark.parametrize("world,d,batch", [(2, 64, 5000), (4, 32, 777), (3, 128, 64)])
+def test_bpr_l2_owner_sharded_equals_the_whole_batch(L, world, d, batch):
+    """dist.train_step's loss at world > 1, replayed on one GPU: every "rank" evaluates the triples of the users in its window of
+    the gathered table (hgr_bpr_l2_fwd_owned_f32), the four sums are added (the all_reduce), and each rank's backward writes its
+    own rows (hgr_bpr_l2_bwd_owned_f32).  Against the oracle on the whole batch: losses to 1e-5, the stacked gradient rows to
+    1e-5 of the largest; the loss is the same on every rank."""
+    rng = np.random.default_rng(world * 1000 + d)
+    n_loc = 96
+    tab = (rng.standard_normal((world * n_loc, d)) * 0.3).astype(np.float32)
+    u = rng.integers(0, world * n_loc, batch)
+    p = rng.integers(0, world * n_loc, batch)
+    n = rng.integers(0, world * n_loc, batch)
+    tu, tp, tn = (torch.from_numpy(v).cuda() for v in (u, p, n))
+    full = torch.from_numpy(tab).cuda()
+    # pass 1: every rank's partial sums (what crosses the ranks)
+    parts = []
+
+    def grab(t):
+        parts.append(t.clone())
+
+    for r in range(world):
+        own = full[r * n_loc:(r + 1) * n_loc].clone().requires_grad_(True)
+        L.bpr_l2_sharded(own, lambda x: full, r * n_loc, tu, tp, tn, 0.05, 2048, grab)
+    total = torch.stack(parts).sum(0)
+    assert all(float(q[0]) > 0 for q in parts)  # every rank owned some triples
+    # pass 2: the step itself, the all_reduce replaced by the precomputed total
+    losses, grads = [], []
+    for r in range(world):
+        own = full[r * n_loc:(r + 1) * n_loc].clone().requires_grad_(True)
+        rec, reg = L.bpr_l2_sharded(own, lambda x: full, r * n_loc, tu, tp, tn, 0.05, 2048, lambda t: t.copy_(total))
+        (2.0 * rec + 3.0 * reg).backward()
+        losses.append(torch.stack([rec.detach(), reg.detach()]))
+        grads.append(own.grad)
+    for q in losses[1:]:
+        assert torch.equal(q, losses[0])
+    o_rec, o_reg, o_du, o_di = O.bpr_l2_from_tables(tab, tab, u, p, n, 0.05, 2048)
+    _, _, du0, di0 = O.bpr_l2_from_tables(tab, tab, u, p, n, 0.0, 2048)
+    want = 2.0 * (du0 + di0) + 3.0 * ((o_du - du0) + (o_di - di0))  # users and items index the same table
+    assert rel_err(losses[0][0], o_rec) < RTOL and rel_err(losses[0][1], o_reg) < RTOL
+    assert grad_err(torch.cat(grads), want) < 2e-5
+    # and the replicated form (every rank evaluates everything) gives the same numbers
+    own = full[:n_loc].clone().requires_grad_(True)
+    rec2, reg2 = L.bpr_l2_sharded(own, lambda x: full, 0, tu, tp, tn, 0.05, 2048)
+    (2.0 * rec2 + 3.0 * reg2).backward()
+    assert rel_err(rec2, losses[0][0]) < 1e-6 and rel_err(reg2, losses[0][1]) < 1e-6
+    assert grad_err(own.grad, grads[0]) < 2e-5
+
+
 def test_reference_signature_bpr_loss_and_bad_indices(L, golden):
     ut, it = golden["loss_user_tab"], golden["loss_item_tab"]
     u, p, n = golden["tri_u"], golden["tri_p"], golden["tri_n"]
