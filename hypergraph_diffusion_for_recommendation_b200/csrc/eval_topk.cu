@@ -394,9 +394,13 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
             if (c.n_my == 0) continue;
             const int64_t row = (int64_t)c.m_blk * EV_BM + half * 128 + quad * 32 + lane;
             const bool live = row < P.n_test;
-            // training items of this user at or after the cell's first column, walked in step with the columns
+            // SAMPLE: training items of this user at or after the cell's first column, walked in step with the columns (the
+            // threshold must not see them).  FILTER leaves them alone: a training item that meets the threshold is appended like
+            // any candidate and dropped by eval_rescore_kernel, which looks every candidate up in the user's training row --
+            // the walk and the 32-way NaN select it feeds cost ~30 % of this pass's instructions when a warp entered them in 62 %
+            // of its chunks (Amazon-Book shape), the look-up costs a few probes of shared memory per candidate.
             int64_t tp = 0, tend = 0;
-            if (live) {
+            if (MODE == EV_SAMPLE && live) {
                 const int32_t u = P.test_users[row];
                 tp = P.train_indptr[u];
                 tend = P.train_indptr[u + 1];
@@ -409,8 +413,8 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
                 }
                 tp = lo;
             }
-            int nt0 = tp < tend ? __ldg(P.train_indices + tp) : INT_MAX;
-            int nt1 = tp + 1 < tend ? __ldg(P.train_indices + tp + 1) : INT_MAX;
+            int nt0 = (MODE == EV_SAMPLE && tp < tend) ? __ldg(P.train_indices + tp) : INT_MAX;
+            int nt1 = (MODE == EV_SAMPLE && tp + 1 < tend) ? __ldg(P.train_indices + tp + 1) : INT_MAX;
 #pragma unroll
             for (int j = 0; j < EV_BUCKETS; ++j) bm[j] = -CUDART_INF_F;
             float thr = CUDART_INF_F;  // FILTER: fixed threshold of this user (a dead row never appends)
@@ -439,7 +443,13 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
                     tc_ld32(tcol + cq * 32, v);
                     tc_ld_wait();
                     const int col0 = col_tile + cq * 32;
-                    if (nt0 < col0 + 32 || col0 + 32 > P.n_items) ev_poison(v, col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
+                    if (MODE == EV_SAMPLE) {
+                        if (nt0 < col0 + 32 || col0 + 32 > P.n_items) ev_poison(v, col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
+                    } else if (col0 + 32 > P.n_items) {  // padding columns of the last tile
+                        int none0 = INT_MAX, none1 = INT_MAX;
+                        int64_t z = 0;
+                        ev_poison(v, col0, P.n_items, none0, none1, z, 0, P.train_indices);
+                    }
                     if (MODE == EV_SAMPLE) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) bm[j] = fmaxf(bm[j], __uint_as_float(v[j]));
@@ -580,8 +590,20 @@ __global__ void __launch_bounds__(128) eval_tau_kernel(const float *__restrict__
 // ------------------------------------------------------------------------------------------ 3. rescore
 constexpr int RS_WARPS = 4;
 constexpr int RS_CAP = 1024;  // candidates of one user held in shared memory
+constexpr int RS_TRAIN = 256; // training items of one user held in shared memory (longer rows are searched in global memory)
 
-// One warp per test user.  (a) the candidates' approximate scores give the approximate K-th best tau_a;
+__device__ __forceinline__ bool sorted_contains(const int32_t *a, int n, int id) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < id) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo < n && a[lo] == id;
+}
+
+// One warp per test user.  (0) candidates that are training items of the user are dropped (the FILTER pass does not mask them);
+// (a) the candidates' approximate scores give the approximate K-th best tau_a;
 // (b) candidates below tau_a - 2 eps cannot be in the exact top-K and are dropped; (c) the survivors are
 // re-scored exactly; (d) K rounds of warp arg-max on (score desc, id asc) keys.
 __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
@@ -592,6 +614,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
     unsigned long long *__restrict__ stats) {
     __shared__ float u_sm[RS_WARPS][128];
     __shared__ unsigned long long keys[RS_WARPS][RS_CAP];
+    __shared__ int32_t train_sm[RS_WARPS][RS_TRAIN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
     if (row >= n_test) return;
@@ -645,6 +668,24 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
             }
         }
     }
+    // (0) training items out: key 0 = no candidate (never selected below, never kept)
+    {
+        const int64_t t0 = train_indptr[u];
+        const int deg = (int)(train_indptr[u + 1] - t0);
+        const int32_t *row_items = train_indices + t0;
+        if (deg > 0 && deg <= RS_TRAIN) {
+            for (int k = lane; k < deg; k += 32) train_sm[warp][k] = row_items[k];
+            row_items = train_sm[warp];
+        }
+        __syncwarp();
+        if (deg > 0) {
+            const int first = row_items[0], last = row_items[deg - 1];
+            for (int j = lane; j < n_c; j += 32) {
+                const int id = (int32_t)(0xffffffffu - (uint32_t)(keys[warp][j] & 0xffffffffu));
+                if (id >= first && id <= last && sorted_contains(row_items, deg, id)) keys[warp][j] = 0ull;
+            }
+        }
+    }
     __syncwarp();
     // K-th best approximate key.  Small lists (the usual case): every lane counts how many keys beat each of its own
     // (keys are unique: the id is part of the key), the key beaten by exactly K - 1 others is the answer.
@@ -694,7 +735,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
         unsigned long long nk = 0ull;
         if (j < n_c) {
             const unsigned long long k = keys[warp][j];
-            ok = k >= keep_key;
+            ok = k != 0ull && k >= keep_key;
             if (ok) {
                 const int id = (int32_t)(0xffffffffu - (uint32_t)(k & 0xffffffffu));
                 const float ex = exact_score(u_sm[warp], item_emb + (int64_t)id * D, D);

@@ -326,3 +326,28 @@ def test_popular_items_with_low_ids_do_not_overflow_the_candidate_lists(E):
     assert np.array_equal(ids[users], want_ids) and np.array_equal(sc[users].view(np.uint32), want_sc.view(np.uint32))
     assert stats[2] == 0, "%d users overflowed their candidate lists" % stats[2]
     assert (ids[:, :k] < 150).mean() > 0.9  # the case really is concentrated
+
+
+def test_training_items_that_pass_the_filter_are_dropped_by_the_rescoring(E):
+    """The FILTER pass does not mask training items: whatever it appends is looked up in the user's training row by the
+    re-scoring kernel.  Users whose training items ARE their best-scoring items (a trained model), with rows short (shared-memory
+    look-up), longer than 256 (global look-up) and long enough to overflow the candidate store (exact fallback): always the
+    oracle's lists, never a training item."""
+    rng = np.random.default_rng(2024)
+    n_users, n_items, d, k = 600, 9000, 64, 20
+    degs = np.concatenate([rng.integers(1, 200, n_users - 6), [300, 500, 900, 1500, 2500, 4000]])
+    tu = np.repeat(np.arange(n_users), degs)
+    ti = np.concatenate([rng.choice(n_items, dg, replace=False) for dg in degs])
+    ptr, idx = train_csr(tu, ti, n_users)
+    ie = (rng.standard_normal((n_items, d)) * 0.1).astype(np.float32)
+    ue = np.zeros((n_users, d), dtype=np.float32)
+    for u in range(n_users):
+        its = idx[ptr[u]:ptr[u + 1]]
+        ue[u] = ie[its[:64]].mean(axis=0) * 3 + 0.02 * rng.standard_normal(d)
+    users = np.arange(n_users, dtype=np.int32)
+    want_ids, want_sc = O.fullrank_topk(ue, ie, users, ptr, idx, k, mode="exact")
+    ids, sc, stats = run(E, ue, ie, users, ptr, idx, k, "exact", "tensor")
+    assert np.array_equal(ids, want_ids) and np.array_equal(sc.view(np.uint32), want_sc.view(np.uint32))
+    for u in (0, n_users - 6, n_users - 3, n_users - 1):
+        assert not np.intersect1d(ids[u], idx[ptr[u]:ptr[u + 1]]).size
+    assert stats[2] < 10  # only the longest rows may take the exact fallback
