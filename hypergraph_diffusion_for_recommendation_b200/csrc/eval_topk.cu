@@ -77,7 +77,8 @@ struct EvalParams {
     const float *thr;    // FILTER in:  [n_test_pad] tau - 2 eps (-inf: no bound)
     float2 *cand;        // FILTER out: [sub * EV_CSPLIT][n_test_pad][cap] (approx score, item id bits): one short list per (sub-range, column half, user)
     int32_t *cand_cnt;   // [sub * EV_CSPLIT][n_test_pad]
-    int32_t *overflow;   // [n_test_pad] flag; [n_test_pad] = count, [n_test_pad + 1 ...] = list of flagged rows
+    int32_t *overflow;   // [n_test_pad] flag; [n_test_pad] = count, [n_test_pad + 2 ...] = list of flagged rows
+                         // ([n_test_pad + 1] = count, [2 n_test_pad + 2 ...] = rows with more than 256 candidates: eval_rescore_kernel)
     int32_t n_test, n_items, n_tiles;
     // Work decomposition.  The item tiles are cut into n_seg segments (SAMPLE: every segment scores its first seg_tiles tiles;
     // FILTER: one segment = the whole catalogue) of `sub` sub-ranges of sub_tiles tiles; a CELL is (sub-range, 256-user block).
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
             }
             if (MODE == EV_FILTER && live) {
                 P.cand_cnt[(int64_t)part * n_pad + row] = min(cnt, P.cap);
-                if (cnt > P.cap && atomicExch(P.overflow + row, 1) == 0) P.overflow[n_pad + 1 + atomicAdd(P.overflow + n_pad, 1)] = (int32_t)row;
+                if (cnt > P.cap && atomicExch(P.overflow + row, 1) == 0) P.overflow[n_pad + 2 + atomicAdd(P.overflow + n_pad, 1)] = (int32_t)row;
             }
         }
     }
@@ -606,17 +607,25 @@ __device__ __forceinline__ bool sorted_contains(const int32_t *a, int n, int id)
 // (a) the candidates' approximate scores give the approximate K-th best tau_a;
 // (b) candidates below tau_a - 2 eps cannot be in the exact top-K and are dropped; (c) the survivors are
 // re-scored exactly; (d) K rounds of warp arg-max on (score desc, id asc) keys.
-__global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
+// Two launches share the users: CAP = 256 (most users: 2 KB of keys per warp, 64 registers, 8 blocks per SM -- the kernel is a chain
+// of dependent memory round trips per warp, so resident warps are what it needs) takes the lists of up to 256 candidates and
+// lists the rows with more; the CAP = RS_CAP launch (LO >= 0) walks that list.
+template <int CAP, int LO, int MINB>
+__global__ void __launch_bounds__(RS_WARPS * 32, MINB) eval_rescore_kernel(
     const float *__restrict__ user_emb, const float *__restrict__ item_emb, int D, const int32_t *__restrict__ test_users,
     const int64_t *__restrict__ train_indptr, const int32_t *__restrict__ train_indices, const float2 *__restrict__ cand,
     const int32_t *__restrict__ cand_cnt, const float *__restrict__ slack, int32_t *__restrict__ overflow, int n_parts,
     int64_t n_pad, int cap, int n_test, int K, int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
     unsigned long long *__restrict__ stats) {
     __shared__ float u_sm[RS_WARPS][128];
-    __shared__ unsigned long long keys[RS_WARPS][RS_CAP];
+    __shared__ unsigned long long keys[RS_WARPS][CAP];
     __shared__ int32_t train_sm[RS_WARPS][RS_TRAIN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (LO >= 0) {  // second launch: the rows the first one listed (one block per RS_WARPS of them; the rest of the grid leaves)
+        if (row >= overflow[n_pad + 1]) return;
+        row = overflow[2 * n_pad + 2 + row];
+    }
     if (row >= n_test) return;
     if (overflow[row]) return;  // handled by eval_brute_kernel
     // list lengths of up to 64 parts, one or two per lane (read once; the copy loop below gets them by shuffle)
@@ -625,8 +634,11 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
     int n_c = cnt_a + cnt_b;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_c += __shfl_xor_sync(0xffffffffu, n_c, o);
-    if (n_c > RS_CAP) {
-        if (lane == 0 && atomicExch(overflow + row, 1) == 0) overflow[n_pad + 1 + atomicAdd(overflow + n_pad, 1)] = (int32_t)row;
+    if (n_c > CAP) {
+        if (lane == 0) {
+            if (CAP < RS_CAP && n_c <= RS_CAP) overflow[2 * n_pad + 2 + atomicAdd(overflow + n_pad + 1, 1)] = (int32_t)row;  // second launch
+            else if (atomicExch(overflow + row, 1) == 0) overflow[n_pad + 2 + atomicAdd(overflow + n_pad, 1)] = (int32_t)row;
+        }
         return;
     }
     const int32_t u = test_users[row];
@@ -690,7 +702,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) eval_rescore_kernel(
     // K-th best approximate key.  Small lists (the usual case): every lane counts how many keys beat each of its own
     // (keys are unique: the id is part of the key), the key beaten by exactly K - 1 others is the answer.
     unsigned long long prev = ~0ull, best = 0ull;
-    if (n_c <= 256) {
+    if (CAP <= 256 || n_c <= 256) {
         unsigned long long mine[8];
         int beat[8];
 #pragma unroll
@@ -833,7 +845,7 @@ __global__ void __launch_bounds__(BF_THREADS) eval_brute_kernel(const float *__r
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_rows = only_overflow ? overflow[n_pad] : n_test;
     for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
-        const int row = only_overflow ? overflow[n_pad + 1 + q] : q;
+        const int row = only_overflow ? overflow[n_pad + 2 + q] : q;
         const int32_t u = test_users[row];
         __syncthreads();
         for (int k = threadIdx.x; k < D; k += BF_THREADS) u_sm[k] = user_emb[(int64_t)u * D + k];
@@ -1005,7 +1017,7 @@ static EvalPlan make_plan(int64_t n_test, int64_t n_items, int D, int K, int eng
         p.off_cand = o; o = align_up(o + (size_t)p.f_sub * EV_CSPLIT * p.n_test_pad * p.cap * 8, 256);
         p.off_cnt = o; o = align_up(o + (size_t)p.f_sub * EV_CSPLIT * p.n_test_pad * 4, 256);
     }
-    p.off_overflow = o; o = align_up(o + (size_t)(2 * p.n_test_pad + 1) * 4, 256);
+    p.off_overflow = o; o = align_up(o + (size_t)(3 * p.n_test_pad + 2) * 4, 256);
     p.off_scratch = o; o = align_up(o + (size_t)p.n_brute_blocks * (size_t)(n_items > 0 ? n_items : 1) * 4, 256);
     p.total = o;
     return p;
@@ -1071,7 +1083,7 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
     int32_t *overflow = reinterpret_cast<int32_t *>(ws + p.off_overflow);
     float *scratch = reinterpret_cast<float *>(ws + p.off_scratch);
     unsigned long long *st64 = reinterpret_cast<unsigned long long *>(stats);
-    HGR_CUDA_OK(cudaMemsetAsync(overflow, 0, (size_t)(p.n_test_pad + 1) * 4, st));
+    HGR_CUDA_OK(cudaMemsetAsync(overflow, 0, (size_t)(p.n_test_pad + 2) * 4, st));
 
     if (p.tensor) {
         __nv_bfloat16 *Ap = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_ap);
@@ -1132,10 +1144,14 @@ int hgr_fullrank_topk_f32(const float *user_emb, int64_t n_users, const float *i
         cells = (int64_t)p.n_mblk * P.sub;
         eval_scores_kernel<EV_FILTER><<<(unsigned)(cells < n_sm ? cells : n_sm), EV_THREADS, smem, st>>>(P);
         HGR_LAUNCH_OK("eval_scores_kernel<filter>");
-        eval_rescore_kernel<<<(unsigned)ceil_div(n_test, RS_WARPS), RS_WARPS * 32, 0, st>>>(
+        eval_rescore_kernel<256, -1, 8><<<(unsigned)ceil_div(n_test, RS_WARPS), RS_WARPS * 32, 0, st>>>(
             user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, slack, overflow,
             p.f_sub * EV_CSPLIT, p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
-        HGR_LAUNCH_OK("eval_rescore_kernel");
+        HGR_LAUNCH_OK("eval_rescore_kernel<256>");
+        eval_rescore_kernel<RS_CAP, 256, 1><<<(unsigned)ceil_div(n_test, RS_WARPS), RS_WARPS * 32, 0, st>>>(
+            user_emb, item_emb, D, test_users, train_indptr, train_indices, P.cand, P.cand_cnt, slack, overflow,
+            p.f_sub * EV_CSPLIT, p.n_test_pad, p.cap, (int)n_test, K, out_ids, out_scores, st64);
+        HGR_LAUNCH_OK("eval_rescore_kernel<1024>");
     }
     eval_brute_kernel<<<(unsigned)p.n_brute_blocks, BF_THREADS, 0, st>>>(user_emb, item_emb, D, (int)n_items, test_users,
                                                                         train_indptr, train_indices, overflow, p.tensor ? 1 : 0,
