@@ -231,11 +231,10 @@ struct EvalSmem {
     static constexpr int END = B + EV_STAGES * 2 * EV_B_BYTES;
 };
 
-// Mark the user's training items (and, in the last tile, the padding columns) among columns
-// [col0, col0 + 32) as NaN: NaN never compares >= a threshold and fmaxf ignores it.  nt0 / nt1 are the next
+// Bit j = column col0 + j is one of the user's training items (or, in the last tile, a padding column).  nt0 / nt1 are the next
 // two training items of the row (software-pipelined: the load of nt1 is in flight while nt0 is used).
-__device__ __forceinline__ void ev_poison(uint32_t (&v)[32], int col0, int n_items, int &nt0, int &nt1, int64_t &tp,
-                                          int64_t tend, const int32_t *__restrict__ train_indices) {
+__device__ __forceinline__ unsigned ev_train_mask(int col0, int n_items, int &nt0, int &nt1, int64_t &tp, int64_t tend,
+                                                  const int32_t *__restrict__ train_indices) {
     unsigned mb = 0;
     if (nt0 < col0 + 32) {
         do {
@@ -246,6 +245,11 @@ __device__ __forceinline__ void ev_poison(uint32_t (&v)[32], int col0, int n_ite
         } while (nt0 < col0 + 32);
     }
     if (col0 + 32 > n_items) mb |= (col0 >= n_items) ? 0xffffffffu : (0xffffffffu << (n_items - col0));
+    return mb;
+}
+
+// SAMPLE: the masked columns become NaN (NaN never compares >= a threshold and fmaxf ignores it) before the running maxima.
+__device__ __forceinline__ void ev_poison(uint32_t (&v)[32], unsigned mb) {
     if (mb) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -259,9 +263,13 @@ __device__ __forceinline__ void ev_poison(uint32_t (&v)[32], int col0, int n_ite
 // global atomicAdd, directly or through a per-warp shared-memory ring drained one tile later: the scoring pass is bound by
 // the instructions its 16 epilogue warps issue, 7 300 -> 11 200 warp instructions per tile, 2.2 -> 2.8 ms at the Amazon-Book
 // shape.)  Branch-free: the four slots are computed up front and the stores are predicated.
+// `masked`: bit q = column col + q is a training item / padding column and is never appended (the FILTER pass does not turn them
+// into NaN first: that 32-way select ran whenever ANY lane of the warp had a training item in the chunk, half of all chunks at
+// the Amazon-Book shape; here the mask costs four bit tests on the rare path).
 __device__ __noinline__ int ev_append4(float x0, float x1, float x2, float x3, float thr, int col, int cnt, int cap,
-                                       float2 *__restrict__ crow) {
-    const bool h0 = x0 >= thr, h1 = x1 >= thr, h2 = x2 >= thr, h3 = x3 >= thr;
+                                       float2 *__restrict__ crow, unsigned masked) {
+    const bool h0 = x0 >= thr && !(masked & 1u), h1 = x1 >= thr && !(masked & 2u), h2 = x2 >= thr && !(masked & 4u),
+               h3 = x3 >= thr && !(masked & 8u);
     const int c0 = cnt, c1 = c0 + (h0 ? 1 : 0), c2 = c1 + (h1 ? 1 : 0), c3 = c2 + (h2 ? 1 : 0);
     if (h0 && c0 < cap) crow[c0] = make_float2(x0, __int_as_float(col));
     if (h1 && c1 < cap) crow[c1] = make_float2(x1, __int_as_float(col + 1));
@@ -395,13 +403,9 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
             if (c.n_my == 0) continue;
             const int64_t row = (int64_t)c.m_blk * EV_BM + half * 128 + quad * 32 + lane;
             const bool live = row < P.n_test;
-            // SAMPLE: training items of this user at or after the cell's first column, walked in step with the columns (the
-            // threshold must not see them).  FILTER leaves them alone: a training item that meets the threshold is appended like
-            // any candidate and dropped by eval_rescore_kernel, which looks every candidate up in the user's training row --
-            // the walk and the 32-way NaN select it feeds cost ~30 % of this pass's instructions when a warp entered them in 62 %
-            // of its chunks (Amazon-Book shape), the look-up costs a few probes of shared memory per candidate.
+            // training items of this user at or after the cell's first column, walked in step with the columns
             int64_t tp = 0, tend = 0;
-            if (MODE == EV_SAMPLE && live) {
+            if (live) {
                 const int32_t u = P.test_users[row];
                 tp = P.train_indptr[u];
                 tend = P.train_indptr[u + 1];
@@ -414,8 +418,8 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
                 }
                 tp = lo;
             }
-            int nt0 = (MODE == EV_SAMPLE && tp < tend) ? __ldg(P.train_indices + tp) : INT_MAX;
-            int nt1 = (MODE == EV_SAMPLE && tp + 1 < tend) ? __ldg(P.train_indices + tp + 1) : INT_MAX;
+            int nt0 = tp < tend ? __ldg(P.train_indices + tp) : INT_MAX;
+            int nt1 = tp + 1 < tend ? __ldg(P.train_indices + tp + 1) : INT_MAX;
 #pragma unroll
             for (int j = 0; j < EV_BUCKETS; ++j) bm[j] = -CUDART_INF_F;
             float thr = CUDART_INF_F;  // FILTER: fixed threshold of this user (a dead row never appends)
@@ -444,19 +448,16 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
                     tc_ld32(tcol + cq * 32, v);
                     tc_ld_wait();
                     const int col0 = col_tile + cq * 32;
+                    unsigned mb = 0;
+                    if (nt0 < col0 + 32 || col0 + 32 > P.n_items) mb = ev_train_mask(col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
                     if (MODE == EV_SAMPLE) {
-                        if (nt0 < col0 + 32 || col0 + 32 > P.n_items) ev_poison(v, col0, P.n_items, nt0, nt1, tp, tend, P.train_indices);
-                    } else if (col0 + 32 > P.n_items) {  // padding columns of the last tile
-                        int none0 = INT_MAX, none1 = INT_MAX;
-                        int64_t z = 0;
-                        ev_poison(v, col0, P.n_items, none0, none1, z, 0, P.train_indices);
-                    }
-                    if (MODE == EV_SAMPLE) {
+                        ev_poison(v, mb);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) bm[j] = fmaxf(bm[j], __uint_as_float(v[j]));
                     } else {
-                        // group maxima first: a user row meets its threshold in ~1 of 30 chunks, and then usually
-                        // in a single group of 4 columns
+                        // group maxima first (over the RAW scores: a masked column that meets the threshold only costs a visit
+                        // of the rare path, where its mask bit keeps it out): a user row meets its threshold in ~1 of 30 chunks,
+                        // and then usually in a single group of 4 columns
                         float m4[8];
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) eval_scores_kernel(const EvalPa
                             for (int g = 0; g < 8; ++g)
                                 if (m4[g] >= thr)
                                     cnt = ev_append4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                                                     __uint_as_float(v[4 * g + 3]), thr, col0 + 4 * g, cnt, P.cap, crow);
+                                                     __uint_as_float(v[4 * g + 3]), thr, col0 + 4 * g, cnt, P.cap, crow, (mb >> (4 * g)) & 15u);
                         }
                     }
                 }
@@ -591,20 +592,8 @@ __global__ void __launch_bounds__(128) eval_tau_kernel(const float *__restrict__
 // ------------------------------------------------------------------------------------------ 3. rescore
 constexpr int RS_WARPS = 4;
 constexpr int RS_CAP = 1024;  // candidates of one user held in shared memory
-constexpr int RS_TRAIN = 256; // training items of one user held in shared memory (longer rows are searched in global memory)
 
-__device__ __forceinline__ bool sorted_contains(const int32_t *a, int n, int id) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] < id) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo < n && a[lo] == id;
-}
-
-// One warp per test user.  (0) candidates that are training items of the user are dropped (the FILTER pass does not mask them);
-// (a) the candidates' approximate scores give the approximate K-th best tau_a;
+// One warp per test user.  (a) the candidates' approximate scores give the approximate K-th best tau_a;
 // (b) candidates below tau_a - 2 eps cannot be in the exact top-K and are dropped; (c) the survivors are
 // re-scored exactly; (d) K rounds of warp arg-max on (score desc, id asc) keys.
 // Two launches share the users: CAP = 256 (most users: 2 KB of keys per warp, 64 registers, 8 blocks per SM -- the kernel is a chain
@@ -619,7 +608,6 @@ __global__ void __launch_bounds__(RS_WARPS * 32, MINB) eval_rescore_kernel(
     unsigned long long *__restrict__ stats) {
     __shared__ float u_sm[RS_WARPS][128];
     __shared__ unsigned long long keys[RS_WARPS][CAP];
-    __shared__ int32_t train_sm[RS_WARPS][RS_TRAIN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
     if (LO >= 0) {  // second launch: the rows the first one listed (one block per RS_WARPS of them; the rest of the grid leaves)
@@ -680,24 +668,6 @@ __global__ void __launch_bounds__(RS_WARPS * 32, MINB) eval_rescore_kernel(
             }
         }
     }
-    // (0) training items out: key 0 = no candidate (never selected below, never kept)
-    {
-        const int64_t t0 = train_indptr[u];
-        const int deg = (int)(train_indptr[u + 1] - t0);
-        const int32_t *row_items = train_indices + t0;
-        if (deg > 0 && deg <= RS_TRAIN) {
-            for (int k = lane; k < deg; k += 32) train_sm[warp][k] = row_items[k];
-            row_items = train_sm[warp];
-        }
-        __syncwarp();
-        if (deg > 0) {
-            const int first = row_items[0], last = row_items[deg - 1];
-            for (int j = lane; j < n_c; j += 32) {
-                const int id = (int32_t)(0xffffffffu - (uint32_t)(keys[warp][j] & 0xffffffffu));
-                if (id >= first && id <= last && sorted_contains(row_items, deg, id)) keys[warp][j] = 0ull;
-            }
-        }
-    }
     __syncwarp();
     // K-th best approximate key.  Small lists (the usual case): every lane counts how many keys beat each of its own
     // (keys are unique: the id is part of the key), the key beaten by exactly K - 1 others is the answer.
@@ -747,7 +717,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, MINB) eval_rescore_kernel(
         unsigned long long nk = 0ull;
         if (j < n_c) {
             const unsigned long long k = keys[warp][j];
-            ok = k != 0ull && k >= keep_key;
+            ok = k >= keep_key;
             if (ok) {
                 const int id = (int32_t)(0xffffffffu - (uint32_t)(k & 0xffffffffu));
                 const float ex = exact_score(u_sm[warp], item_emb + (int64_t)id * D, D);
