@@ -154,6 +154,60 @@ def _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner
     return torch.cat([ids[order], empty.to(torch.int32)]).contiguous()
 
 
+def _spread_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz, window_rows, chunk_start=None):
+    """The windowed order for the chunks, with the whole rows SPREAD evenly through it instead of sitting in the window of their
+    first column.  For a row-partitioned block whose propagation publishes every finished row to all ranks (fused all-gather):
+    the whole rows are most of the output rows, and in the windowed order they all run in the first windows (every user row starts
+    in rank 0's item range), so the exchange is squeezed into the first half of the kernel and stalls it.  Here runs of ``_RUN``
+    rows of equal length (a whole thread block) are shuffled with a fixed seed and merged with the chunk runs in proportion to
+    their nonzeros: finished rows -- and the NVLink traffic they cause -- leave at a steady rate from the first block to the last."""
+    dev = indptr.device
+    n_rows = indptr.numel() - 1
+    deg = indptr[1:] - indptr[:-1]
+    n_chunks = int(chunk_owner.numel())
+    light = torch.ones(n_rows, dtype=torch.bool, device=dev)
+    if heavy_rows.numel():
+        light[heavy_rows.long()] = False
+    rows = torch.nonzero(light & (deg > 0)).flatten()
+    empty = torch.nonzero(light & (deg == 0)).flatten()
+    if n_chunks == 0 or rows.numel() == 0:
+        return _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz, window_rows, chunk_start)
+    # chunks: window of the first column, then descending length
+    own = chunk_owner.long()
+    row_end = indptr[heavy_rows.long()[own] + 1]
+    if chunk_start is not None:
+        c_start = chunk_start
+        last = torch.arange(1, n_chunks + 1, device=dev) == heavy_chunk_ptr[own + 1]
+        c_len = torch.where(last, row_end, torch.cat([chunk_start[1:], chunk_start[:1]])) - c_start
+    else:
+        c_start = indptr[heavy_rows.long()[own]] + (torch.arange(n_chunks, device=dev) - heavy_chunk_ptr[own]) * chunk_nnz
+        c_len = torch.clamp(row_end - c_start, max=chunk_nnz)
+    big = int(deg.max()) + 2
+    c_order = torch.sort((indices[c_start].long() // window_rows) * big + (big - c_len), stable=True).indices
+    c_ids = (~torch.arange(n_chunks, dtype=torch.int32, device=dev))[c_order]
+    c_len = c_len[c_order]
+    # rows: runs of equal length, shuffled
+    r_order = torch.sort(deg[rows], descending=True, stable=True).indices
+    rows = rows[r_order]
+    n_runs = -(-int(rows.numel()) // _RUN)
+    gen = torch.Generator()
+    gen.manual_seed(0x5eed)
+    run_pos = torch.empty(n_runs, dtype=torch.long)
+    run_pos[torch.randperm(n_runs, generator=gen)] = torch.arange(n_runs)
+    slot = run_pos.to(dev)[torch.arange(rows.numel(), device=dev) // _RUN] * _RUN + torch.arange(rows.numel(), device=dev) % _RUN
+    rows = rows[torch.sort(slot).indices]
+    r_len = deg[rows]
+
+    def run_keys(lengths):  # fraction of the list's nonzeros that precede the run an entry belongs to
+        n = lengths.numel()
+        before = torch.cumsum(lengths, 0) - lengths
+        first = before[torch.arange(0, n, _RUN, device=dev)]
+        return first.to(torch.float64)[torch.arange(n, device=dev) // _RUN] / max(float(lengths.sum()), 1.0)
+
+    merged = torch.sort(torch.cat([run_keys(c_len), run_keys(r_len)]), stable=True).indices  # ties: the chunk run first
+    return torch.cat([torch.cat([c_ids, rows.to(torch.int32)])[merged], empty.to(torch.int32)]).contiguous()
+
+
 def work_schedule(indptr: torch.Tensor, heavy_rows: torch.Tensor, n_chunks: int, chunk_nnz: int, mode: str,
                   indices: torch.Tensor | None = None, heavy_chunk_ptr: torch.Tensor | None = None,
                   chunk_owner: torch.Tensor | None = None, n_cols: int = 0, chunk_start: torch.Tensor | None = None) -> torch.Tensor | None:
@@ -166,6 +220,8 @@ def work_schedule(indptr: torch.Tensor, heavy_rows: torch.Tensor, n_chunks: int,
                      (mostly popular items gathering from the large user table: DRAM-bound) and rows (mostly users
                      gathering from the L2-resident item table) are in flight together instead of one after the other.
     ``windowed[:W]`` items ordered by the W-row window of the gathered table their first column falls in (``_windowed_schedule``).
+    ``spread[:W]``   the windowed order for the chunks, whole rows spread evenly through it (``_spread_schedule``): the schedule of a
+                     row-partitioned block whose kernel publishes its rows to many ranks.
     ``auto``         ``windowed`` when the gathered table is larger than 64 MB, else ``binned`` (the default).
     ``stored``       no list (rows in stored order, chunk blocks first).
 
@@ -177,6 +233,9 @@ def work_schedule(indptr: torch.Tensor, heavy_rows: torch.Tensor, n_chunks: int,
         mode = "windowed" if n_cols * 256 > (64 << 20) else "binned"
     if mode == "stored":
         return None
+    if mode.startswith("spread"):
+        return _spread_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz,
+                                int(mode.split(":")[1]) if ":" in mode else _WINDOW_ROWS, chunk_start)
     if mode.startswith("windowed"):
         return _windowed_schedule(indptr, indices, heavy_rows, heavy_chunk_ptr, chunk_owner, chunk_nnz,
                                   int(mode.split(":")[1]) if ":" in mode else _WINDOW_ROWS, chunk_start)

@@ -141,7 +141,7 @@ def test_shape_predicates_refuse_cpu_tensors_and_odd_widths():
         ops.hyperedge(torch.ones(8, 128), torch.ones(8, 64))
 
 
-@pytest.mark.parametrize("mode", ["binned", "interleaved", "windowed", "windowed:7", "auto"])
+@pytest.mark.parametrize("mode", ["binned", "interleaved", "windowed", "windowed:7", "spread", "spread:7", "auto"])
 def test_work_schedule_lists_every_row_and_chunk_once(mode):
     """hgr_csr_t::work_order: whatever the order, each unsplit row and each chunk of the split plan appears exactly once."""
     import numpy as np
