@@ -5,7 +5,7 @@
 Runs `ncu --metrics ... --clock-control none -k regex:<kernel> -c <n>` over the probe scripts (one GPU; never a bench number)
 and writes, keyed the way bench.py looks them up (`profiles/kernel_counters.json` after the file is copied there):
 
-  spmm:<workload>:<world>:<schedule>   dram_read_bytes, dram_write_bytes, l2_to_sm_bytes, l2_hit_pct, duration_ms
+  spmm:<workload>:<world>:<schedule>   (schedule = what DeviceCSR.schedule reports: auto, or spread for the blocks of >= 4 ranks) dram_read_bytes, dram_write_bytes, l2_to_sm_bytes, l2_hit_pct, duration_ms
   eval:<workload>:<world>              per scoring kernel: tensor-pipe cycles active as % of peak sustained ELAPSED, duration
 """
 import argparse
@@ -30,6 +30,8 @@ JOBS = {
     "spmm_c5w8": ("spmm:c5w:8", "spmm_rows_async", 1, ["tools/shard_probe.py", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
     "spmm_c5w4": ("spmm:c5w:4", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "4", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
     "spmm_c5w2": ("spmm:c5w:2", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "2", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
+    "spmm_c5w8s": ("spmm:c5w:8", "spmm_rows_async", 1, ["tools/shard_probe.py", "--schedules", "spread", "--splits", "auto", "--iters", "1"]),
+    "spmm_c5w4s": ("spmm:c5w:4", "spmm_rows_async", 1, ["tools/shard_probe.py", "--world", "4", "--schedules", "spread", "--splits", "auto", "--iters", "1"]),
     "spmm_c4": ("spmm:c4:1", "spmm_rows_async", 1, ["tools/spmm_probe.py", "--shapes", "52000x92000x3000000", "--variants", "0", "--schedules", "auto", "--splits", "auto", "--iters", "1"]),
     "eval_c5w": ("eval:c5w:1", "eval_scores", 2, ["tools/eval_probe.py", "--shape", "c5e", "--users", "262144", "--iters", "1"]),
     "eval_c4": ("eval:c4:1", "eval_scores", 2, ["tools/eval_probe.py", "--shape", "c4", "--iters", "1"]),
@@ -76,7 +78,7 @@ def main():
         if prefix.startswith("spmm"):
             (_, kname), m = next(iter(launches.items()))
             # the schedule `auto` resolves to for this shape (graph.work_schedule): windowed above a 64 MB table, else binned
-            sched = "auto"
+            sched = cmd[cmd.index("--schedules") + 1] if "--schedules" in cmd else "auto"
             out["%s:%s" % (prefix, sched)] = {
                 "kernel": kname.split("(")[0], "dram_read_bytes": m["dram__bytes_read.sum"], "dram_write_bytes": m["dram__bytes_write.sum"],
                 "l2_to_sm_bytes": m["l1tex__m_xbar2l1tex_read_bytes.sum"], "l2_hit_pct": m["lts__t_sector_hit_rate.pct"],
