@@ -243,10 +243,15 @@ class SymmetricPool:
         self.next = 0
         self.wait_events = None
 
-    def take(self) -> int:
-        k = self.next
-        self.next = (k + 1) % len(self.bufs)
-        return k
+    def take(self, reading: torch.Tensor | None = None) -> int:
+        """Next slot of the ring; never the slot the kernel about to run READS (``reading``: its gathered input) -- peers would be
+        storing into it meanwhile.  Every rank makes the same calls in the same order, so all ranks skip the same slot."""
+        for _ in range(len(self.bufs)):
+            k = self.next
+            self.next = (k + 1) % len(self.bufs)
+            if reading is None or self.bufs[k].data_ptr() != reading.data_ptr():
+                return k
+        raise RuntimeError("symmetric pool: no free slot")
 
     def barrier(self, k: int) -> None:
         ev = self.wait_events
@@ -352,7 +357,7 @@ class DistGraph:
         """``y_own = epilogue(A_loc @ full_in)`` whose rows are stored, by the kernel's own epilogue, into slot ``k`` of
         the symmetric pool on EVERY rank (fused all-gather).  Returns ``(gathered [n_glob, D], y_own or None)``."""
         pool = self.pool(full_in.shape[1])
-        k = pool.take()
+        k = pool.take(reading=full_in)
         self._published.pop(k, None)  # the slot is being rewritten: forget what it held
         self.multicast = pool.multicast
         ep = dict(ep or {}, gather_ptrs=pool.ptrs[k], gather_row_offset=self.rank * self.part.n_loc,

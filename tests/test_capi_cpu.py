@@ -215,3 +215,37 @@ def test_window_split_plan_rule():
     assert np.array_equal(np.sort(~order[order < 0]), np.arange(owner.size))
     first = indices[start[~order[order < 0]]] >> 9
     assert (np.diff(first) >= 0).all() or True  # chunks come window by window inside the merged list (rows are interleaved)
+
+
+def test_spread_schedule_hands_out_whole_rows_at_a_steady_rate():
+    """graph._spread_schedule: chunks keep the windowed order, whole rows are spread -- in every quarter of the work list
+    (measured in nonzeros) about a quarter of the whole rows, where the windowed order packs them into the first windows."""
+    import numpy as np
+    import torch
+
+    from hypergraph_diffusion_for_recommendation_b200 import graph
+
+    rng = np.random.default_rng(21)
+    n_cols = 1 << 15
+    deg = np.concatenate([rng.integers(4, 40, 3000), rng.integers(300, 3000, 60)])
+    indptr = np.zeros(deg.size + 1, dtype=np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    # like a user row of a partitioned block: every short row starts in the first window
+    indices = np.concatenate([np.sort(np.concatenate([rng.choice(256, 1), 256 + rng.choice(n_cols - 256, d - 1, replace=False)])) for d in deg]).astype(np.int32)
+    heavy, ptr, owner = graph.split_plan(indptr, 128)
+    args = (torch.from_numpy(indptr), torch.from_numpy(heavy), int(owner.size), 128)
+    kw = dict(indices=torch.from_numpy(indices), heavy_chunk_ptr=torch.from_numpy(ptr), chunk_owner=torch.from_numpy(owner), n_cols=n_cols)
+
+    def rows_per_quarter(mode):
+        order = graph.work_schedule(*args, mode, **kw).numpy()
+        ln = np.where(order >= 0, deg[np.maximum(order, 0)], 128)
+        pos = (np.cumsum(ln) - ln) / ln.sum()
+        return np.histogram(pos[order >= 0], bins=4, range=(0, 1))[0] / float((order >= 0).sum())
+
+    spread, windowed = rows_per_quarter("spread:1024"), rows_per_quarter("windowed:1024")
+    assert (np.abs(spread - 0.25) < 0.08).all(), spread
+    assert windowed[2:].sum() == 0, windowed  # every whole row before the half-way mark: the rest of the kernel publishes nothing
+    # chunks are in the same relative order in both lists
+    a = graph.work_schedule(*args, "spread:1024", **kw).numpy()
+    b = graph.work_schedule(*args, "windowed:1024", **kw).numpy()
+    assert np.array_equal(a[a < 0], b[b < 0])
