@@ -2,8 +2,9 @@
 //
 // Why: the propagation gathers one 256-byte embedding row per nonzero.  When the gathered table is larger than L2 (the 320 MB
 // user table of the 1.25 M x 0.25 M graph, the 3 GB table of an 8-GPU block), a row whose columns span the whole table misses
-// L2 on almost every gather -- unless all rows walk the table together, window by window.  A chunk of this plan lies inside
-// one window of 2^window_shift table rows (or is shorter than min_seg / capped at max_seg); the work list orders chunks by
+// L2 on almost every gather -- unless all rows walk the table together, window by window.  A chunk of this plan ends where its
+// row leaves a window of 2^window_shift table rows, once it holds min_seg nonzeros (and at max_seg at the latest: a chunk of a
+// dense row lies inside one window, a chunk of a sparse row spans the few windows its min_seg nonzeros need); the work list orders chunks by
 // window (graph.py: _windowed_schedule), so a window is read from DRAM once and then served from L2 to every row that
 // references it.  The partial rows cost 512 bytes of traffic per chunk, far less than the ~min_seg x 256 bytes they save.
 //
